@@ -1,0 +1,275 @@
+"""Known-answer tests that pin the CPU oracle.
+
+The reference has no tests or golden vectors and cannot be compiled here, so
+these mathematical identities, plus an independently written numpy model
+(tests/np_model.py), are what the oracle is pinned against.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import np_model
+import oracle_lib as ol
+
+
+@pytest.fixture(scope="module")
+def lib():
+    ol.build_oracle()
+    return ol.load()
+
+
+def gen_matrix(lib, M, Cc, row, col, p):
+    n = row * col
+    A = np.zeros(5 * n); rhs = np.zeros(n); ioff = np.zeros(5, np.int32)
+    lib.oracle_gen_matrix(M, Cc, A, ioff, rhs, row, col, C.byref(p))
+    return A.reshape(5, n), ioff, rhs
+
+
+def dia_to_dense(A, ioff, n):
+    D = np.zeros((n, n))
+    for k in range(5):
+        for i in range(n):
+            j = i + ioff[k]
+            if 0 <= j < n:
+                D[i, j] += A[k, i]
+    return D
+
+
+@pytest.mark.parametrize("m,e", [(0.3, 4), (0.7, 6), (1.3, 1), (0.5, 0), (2.0, 7), (0.9, -3)])
+def test_powi_is_binary_exponentiation(lib, m, e):
+    got = lib.oracle_powi(m, e)
+    assert got == pytest.approx(m ** e, rel=4e-16 * max(1, abs(e)))
+    if e == 4:
+        assert got == (m * m) * (m * m)      # libgcc order for e = 4
+
+
+def test_ffunc_dfunc_selects(lib):
+    M, Cc, k, nu = 0.37, 0.81, 0.01, 0.3
+    eps = Cc * 1e-8
+    want = {1: Cc / (k + Cc) - nu, 2: Cc / (k + Cc), 3: Cc / (k * M + Cc + eps) - nu,
+            4: Cc / (k * M + Cc + eps), 5: 1.0,
+            6: Cc / (k + Cc) * (1 - M / (Cc + eps)) - nu}
+    for fs, w in want.items():
+        assert lib.oracle_ffunc(M, Cc, k, nu, fs) == pytest.approx(w, rel=1e-15)
+    assert lib.oracle_dfunc(M, 1e-4, 4, 4, 1) == 1e-4
+    assert lib.oracle_dfunc(M, 1e-4, 4, 4, 2) == pytest.approx(1e-4 * M ** 4, rel=1e-15)
+    assert lib.oracle_dfunc(M, 1e-4, 4, 6, 3) == pytest.approx(
+        1e-4 * M ** 4 / (1 - M) ** 6, rel=1e-15)
+
+
+@pytest.mark.parametrize("row,col", [(5, 5), (7, 4), (9, 6), (6, 11)])
+@pytest.mark.parametrize("fsel,dsel", [(1, 3), (3, 2), (6, 1), (5, 3)])
+def test_K1_row_sum_identity(lib, row, col, fsel, dsel):
+    """A.1 = 1/tDel - f per row (every face coefficient is subtracted
+    off-diagonal and added on-diagonal, P:553-581), quirk cell included."""
+    rng = np.random.RandomState(row * 100 + col)
+    n = row * col
+    M = rng.uniform(0.05, 0.8, n); Cc = rng.uniform(0.2, 1.0, n)
+    p = ol.default_params(row, fSelect=fsel, dSelect=dsel)
+    A, ioff, rhs = gen_matrix(lib, M, Cc, row, col, p)
+    D = dia_to_dense(A, ioff, n)
+    f = np_model.ffunc(M, Cc, p)
+    want = 1.0 / p.tDel - f
+    scale = np.abs(D).sum(axis=1)
+    assert np.all(np.abs(D.sum(axis=1) - want) <= 1e-13 * scale)
+    assert np.array_equal(rhs, M / p.tDel)
+    assert list(ioff) == [-col, -1, 0, 1, col]
+
+
+@pytest.mark.parametrize("row,col", [(5, 5), (7, 4), (6, 9)])
+def test_operator_matches_independent_model(lib, row, col):
+    rng = np.random.RandomState(7)
+    n = row * col
+    M = rng.uniform(0.0, 0.85, n); Cc = rng.uniform(0.1, 1.0, n)
+    p = ol.default_params(row)
+    A, ioff, _ = gen_matrix(lib, M, Cc, row, col, p)
+    D = dia_to_dense(A, ioff, n)
+    W = np_model.dense_operator(M, Cc, row, col, p)
+    assert np.allclose(D, W, rtol=1e-13, atol=1e-13 * np.abs(W).max())
+
+
+def test_K3_structure_and_quirk(lib):
+    """Reflecting boundaries: A is non-symmetric exactly at boundary cells and
+    W.A (trapezoid weights) is symmetric except entries touching cell n-col
+    (1-based), whose last-row treatment is the reference's '>=' quirk."""
+    row = col = 5
+    n = row * col
+    rng = np.random.RandomState(3)
+    M = rng.uniform(0.1, 0.8, n); Cc = np.ones(n)
+    p = ol.default_params(row)
+    A, ioff, _ = gen_matrix(lib, M, Cc, row, col, p)
+    D = dia_to_dense(A, ioff, n)
+    q = n - col - 1                       # 0-based index of the quirk cell
+    # quirk cell: no south / east coupling, doubled north / west coupling
+    h = 0.5 / (p.xDel ** 2)
+    d = np_model.dfunc(M, p)
+    assert D[q, q + col] == 0.0 and D[q, q + 1] == 0.0
+    assert D[q, q - col] == pytest.approx(-2 * h * (d[q - col] + d[q]), rel=1e-15)
+    assert D[q, q - 1] == pytest.approx(-2 * h * (d[q - 1] + d[q]), rel=1e-15)
+    w_r = np.ones(row); w_r[[0, -1]] = 0.5
+    w_c = np.ones(col); w_c[[0, -1]] = 0.5
+    W = np.outer(w_r, w_c).ravel()
+    S = W[:, None] * D
+    asym = np.abs(S - S.T)
+    asym[q, :] = 0; asym[:, q] = 0
+    assert asym.max() <= 1e-12 * np.abs(S).max()
+    # interior rows are symmetric on their own, first row is not
+    assert D[0, col] != D[col, 0]
+    i = 2 * col + 2
+    assert D[i, i + 1] == D[i + 1, i]
+
+
+def test_amuxd_matches_dense(lib):
+    row, col = 6, 5
+    n = row * col
+    rng = np.random.RandomState(11)
+    M = rng.uniform(0.1, 0.8, n); Cc = rng.uniform(0.1, 1, n)
+    p = ol.default_params(row)
+    A, ioff, _ = gen_matrix(lib, M, Cc, row, col, p)
+    x = rng.standard_normal(n); y = np.empty(n)
+    lib.oracle_amuxd(n, x, y, np.ascontiguousarray(A.ravel()), 5, ioff)
+    want = dia_to_dense(A, ioff, n) @ x
+    assert np.allclose(y, want, rtol=1e-13, atol=1e-13 * np.abs(want).max())
+
+
+def test_cg_matches_independent_cg(lib):
+    row = col = 17
+    n = row * col
+    M, Cc = ol.ic1(row, col, 0.9, 0.3)
+    p = ol.default_params(row)
+    A, ioff, rhs = gen_matrix(lib, M, Cc, row, col, p)
+    sol = np.zeros(n); scratch = np.zeros(3 * n)
+    nit = C.c_longlong(100 * n); e1 = C.c_double(p.e1); e2 = C.c_double(p.e2)
+    stop = C.c_int(0)
+    lib.oracle_solve_ls_diag(n, 5, ioff, np.ascontiguousarray(A.ravel()), sol, rhs,
+                             C.byref(nit), C.byref(e1), C.byref(e2), C.byref(stop),
+                             scratch, None, 0)
+    D = np_model.dense_operator(M, Cc, row, col, p)
+    x, it = np_model.cg_reference(D, rhs, np.zeros(n), p.e2, 100 * n)
+    assert stop.value == -100
+    assert nit.value == it
+    assert np.linalg.norm(sol - x) <= 1e-12 * np.linalg.norm(x)
+    # and it really solves the system to the solver's tolerance
+    assert np.linalg.norm(D @ sol - rhs) <= 1e-6 * np.linalg.norm(rhs)
+
+
+def test_solve_c_is_trapezoid_root(lib):
+    rng = np.random.RandomState(5)
+    n = 200
+    Mp = rng.uniform(0, 0.9, n); Mn = rng.uniform(0, 0.9, n); Cp = rng.uniform(0.01, 1, n)
+    p = ol.default_params(16)
+    Cn = np.empty(n)
+    lib.oracle_solve_c(Mp, Mn, Cp, Cn, n, p.kappa, p.gama, p.tDel, 1)
+    assert np.allclose(Cn, np_model.solve_c(Mp, Mn, Cp, p), rtol=1e-14)
+    g = lambda Cc, M: p.gama * M * Cc / (p.kappa + Cc)
+    resid = Cn - Cp + 0.5 * p.tDel * (g(Cn, Mn) + g(Cp, Mp))
+    assert np.abs(resid).max() < 1e-15 * 50
+
+
+def test_K2_homogeneous_state(lib):
+    """MinitialCond = 2: fields stay uniform, M = M0/(1 - tDel f(C)), Picard 2,
+    CG 2 iterations for the first solve and 1 for the second."""
+    row = col = 33
+    p = ol.default_params(row)
+    M0, C0 = ol.ic2(row, col, 0.02)
+    o = ol.Oracle(row, col, p)
+    o.set_state(M0, C0)
+    m, c = 0.02, 1.0
+    for step in range(4):
+        r = o.step()
+        assert r["rc"] == 0 and r["countIters"] == 2
+        assert r["nits"] == [2, 1]
+        # scalar recurrence of the scheme
+        ck = c
+        for _ in range(2):
+            f = ck / (p.kappa + ck) - p.nu
+            mk = m / (1 - p.tDel * f)
+            aux = 0.5 * p.tDel * p.gama
+            b = p.kappa - c + aux * (mk + c * m / (p.kappa + c))
+            cc = -p.kappa * c + aux * p.kappa * c * m / (p.kappa + c)
+            ck = 0.5 * (-b + np.sqrt(b * b - 4 * cc))
+        m, c = mk, ck
+        M, Cc = o.get_state()
+        assert M.max() - M.min() < 1e-15 and Cc.max() - Cc.min() < 1e-15
+        assert M[0] == pytest.approx(m, rel=1e-12)
+        assert Cc[0] == pytest.approx(c, rel=1e-12)
+
+
+def test_K6_warm_start(lib):
+    """x0 = previous contents of Mnew (P:714): the second Picard solve of a
+    step needs far fewer CG iterations than the first."""
+    row = col = 65
+    p = ol.default_params(row)
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    o = ol.Oracle(row, col, p)
+    o.set_state(M0, C0)
+    r = o.step()
+    assert r["countIters"] >= 2
+    assert r["nits"][0] > 10 * r["nits"][1]
+    assert r["nitSum"] == sum(r["nits"]) and r["nitMax"] == max(r["nits"])
+    # Picard stop rule (P:706): last diffs below eSoln, earlier ones above
+    dC, dM = r["diffs"][-1]
+    assert dC + dM <= p.eSoln
+    assert all(a + b > p.eSoln for a, b in r["diffs"][:-1])
+
+
+def test_first_iteration_never_stops(lib):
+    """With x0 = 0, normx = 0 in iteration 1, so err2 < tol2*normx is false
+    and at least 2 iterations run."""
+    row = col = 9
+    p = ol.default_params(row)
+    M0, C0 = ol.ic2(row, col, 0.5)
+    o = ol.Oracle(row, col, p)
+    o.set_state(M0, C0)
+    nit, tr = o.first_solve_trace()
+    assert nit >= 2 and tr[0]["normx"] == 0.0
+
+
+def test_cg_iteration_cap(lib):
+    row = col = 33
+    p = ol.default_params(row)
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    o = ol.Oracle(row, col, p)
+    o.set_state(M0, C0)
+    o.set_maxit(5)
+    nit, _ = o.first_solve_trace()
+    assert nit == 6                        # CG:88 tests nit > maxit after the update
+
+
+def test_peak_interface_semantics(lib):
+    row, col = 6, 4
+    M = np.zeros(row * col)
+    M[1 * col + 2] = 0.5; M[3 * col + 0] = 0.5       # tie: last maximal cell wins (P:993)
+    M[4 * col + 1] = 0.2
+    pk, he, itf = C.c_double(-1), C.c_double(-1), C.c_double(-7)
+    lib.oracle_calc_peak_interface(M, row, col, C.byref(pk), C.byref(he), C.byref(itf))
+    assert he.value == 0.5 and pk.value == 3 / 5 and itf.value == 4 / 5
+    M[:] = 0.05
+    itf = C.c_double(-7)
+    lib.oracle_calc_peak_interface(M, row, col, C.byref(pk), C.byref(he), C.byref(itf))
+    assert itf.value == -7.0               # never assigned when no M > 0.1 (D8)
+    assert pk.value == 1.0                 # '>=' walks to the last cell
+
+
+def test_mass_and_diff(lib):
+    rng = np.random.RandomState(2)
+    a = rng.rand(35); b = rng.rand(35)
+    assert lib.oracle_calc_mass(a, 35) == pytest.approx(a.mean(), rel=1e-15)
+    assert lib.oracle_calc_diff(a, b, 7, 5) == pytest.approx(np.abs(a - b).mean(), rel=1e-15)
+
+
+def test_openmp_build_agrees(lib):
+    row = col = 33
+    p = ol.default_params(row)
+    M0, C0 = ol.ic_blobs(row, col, 0.4, 0.2, 6, 1)
+    res = []
+    for omp in (False, True):
+        o = ol.Oracle(row, col, p, omp=omp)
+        o.set_state(M0, C0)
+        info = [o.step() for _ in range(3)]
+        res.append((o.get_state(), [i["nits"] for i in info]))
+    (Ma, Ca), na = res[0]; (Mb, Cb), nb = res[1]
+    assert na == nb
+    assert np.linalg.norm(Ma - Mb) <= 1e-12 * np.linalg.norm(Ma)
+    assert np.linalg.norm(Ca - Cb) <= 1e-12 * np.linalg.norm(Ca)
