@@ -1,0 +1,168 @@
+/*
+ * pdeode_b200.h -- C ABI of libpdeode_b200.so: the implicit 2-D time step of
+ * ericmjalbert/PDE-ODEsolver on NVIDIA B200 (sm_100a), fp64.
+ *
+ * The reference has no plugin / FFI interface: its Fortran subroutines are
+ * called directly (only interface block: PDE-ODEsolver.f90:23-51).  The seam
+ * this library replaces is the loop body of solveOrder2
+ * (PDE-ODEsolver.f90:700-742) plus the in-loop diagnostics
+ * (PDE-ODEsolver.f90:667-668,677).  The ABI is step-granular with
+ * device-resident state: the caller uploads M and C once, calls
+ * pdeode_step() per time step, and downloads fields only at frame times.
+ * Each entry point cites the reference lines it stands in for.
+ *
+ * "P:" = PDE-ODEsolver.f90, "CG:" = CGdiag.f90 in the reference.
+ *
+ * Conventions
+ *   - plain C types only; the caller owns host arrays, the library owns all
+ *     device memory, streams and communicators; no pointer outlives a call.
+ *   - fields are row-major, cell p = j + i*col (0-based; P:838 1-based),
+ *     row*col doubles (the reference build is -fdefault-real-8).
+ *   - every function returns 0 (PDEODE_OK) or an error code below; nothing
+ *     aborts inside the library.  pdeode_step may OR PDEODE_WARN_CG_CAP into
+ *     an otherwise-OK return (the reference ignores its CG cap, P:714).
+ *   - there is no CPU fallback: without a CUDA device every compute entry
+ *     point returns PDEODE_ERR_NODEVICE.
+ *   - one context is not re-entrant; use one context per host thread / rank.
+ */
+#ifndef PDEODE_B200_H
+#define PDEODE_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PDEODE_OK              0
+#define PDEODE_ERR_CUDA        1   /* a CUDA call failed; see pdeode_last_error */
+#define PDEODE_ERR_NCCL        2
+#define PDEODE_ERR_ARG         3
+#define PDEODE_ERR_PICARD_CAP  4   /* countIters > 10000 (P:732-736): the host
+                                      prints the two lines of P:733-734 and stops */
+#define PDEODE_ERR_NOMEM       5
+#define PDEODE_ERR_NODEVICE    6
+#define PDEODE_ERR_MASK        0xff
+#define PDEODE_WARN_CG_CAP     0x100 /* some solve hit nit > maxit (CG:88) */
+
+#define PDEODE_NCCL_ID_BYTES   128
+
+typedef struct pdeode_ctx pdeode_ctx;
+
+/* The numerical parameters solveOrder2 receives (P:600-611).  xDel is what the
+ * host computed at P:110 (1/row); e1 is carried for completeness (criterion 1
+ * is commented out in the reference, CG:89). */
+typedef struct {
+    double delta, nu, kappa, gama; /* P:61 */
+    double tDel, xDel;             /* P:69 */
+    double e1, e2, eSoln;          /* P:69 */
+    int alpha, beta;               /* P:62, integer exponents of D(M) */
+    int dSelect, fSelect, gSelect; /* P:64 */
+    int reserved;                  /* must be 0 */
+} pdeode_params;
+
+/* ---- lifetime ------------------------------------------------------- */
+
+/* Allocates device state for a row x col grid on CUDA device `device`
+ * (P:133, P:623-628).  The CG warm start Mnew is zero.
+ * Requires row >= 3, col >= 2. */
+int pdeode_create(pdeode_ctx **ctx, int row, int col, const pdeode_params *p,
+                  int device);
+
+/* Row-slab member of an nranks-wide solve: rank r owns global rows
+ * [r*row/nranks, (r+1)*row/nranks).  id = PDEODE_NCCL_ID_BYTES bytes produced
+ * by pdeode_nccl_unique_id on rank 0 and distributed by the caller (the
+ * reference has no multi-process mode; this extends P:700-742 across GPUs). */
+int pdeode_create_dist(pdeode_ctx **ctx, int row, int col,
+                       const pdeode_params *p, int device, int rank,
+                       int nranks, const void *id);
+int pdeode_nccl_unique_id(void *id_out);
+
+int pdeode_destroy(pdeode_ctx *ctx);
+
+/* Global rows owned by this context: [*row0, *row0 + *nrows). */
+int pdeode_local_rows(const pdeode_ctx *ctx, int *row0, int *nrows);
+
+/* Launch on this cudaStream_t (as void*) from now on; NULL = the library's
+ * own stream. */
+int pdeode_set_stream(pdeode_ctx *ctx, void *cuda_stream);
+
+/* ---- state ---------------------------------------------------------- */
+
+/* H2D of this context's slab (nrows*col doubles each; the whole grid for a
+ * single-GPU context).  Resets the CG warm start to zero, as a fresh call of
+ * solveOrder2 would (P:133-138, P:623). */
+int pdeode_set_state(pdeode_ctx *ctx, const double *M, const double *C);
+
+/* D2H of this context's slab; needed at frame times only (P:685-687). */
+int pdeode_get_state(pdeode_ctx *ctx, double *M, double *C);
+
+/* ---- the path ------------------------------------------------------- */
+
+/* One implicit time step, Picard loop included (P:700-742).  Returns this
+ * step's Picard count and CG totals so the host can keep avgIters, maxIters,
+ * avgNit, maxNit exactly as P:722-723,739-740 do. */
+int pdeode_step(pdeode_ctx *ctx, int *countIters, long long *nitSum,
+                long long *nitMax);
+
+/* calcMass(M), calcMass(C) (P:667-668, P:772-791): grid means, global over
+ * all ranks. */
+int pdeode_mass(pdeode_ctx *ctx, double *meanM, double *meanC);
+
+/* calcPeakInterface (P:677, P:978-1004).  peak / intfac are left untouched
+ * when the reference would not assign them. */
+int pdeode_peak(pdeode_ctx *ctx, double *peak, double *height, double *intfac);
+
+/* ---- knobs and introspection (no reference counterpart) -------------- */
+
+/* CG iteration cap; default 100*n (P:707).  < 0 restores the default. */
+int pdeode_set_maxit(pdeode_ctx *ctx, long long maxit);
+
+/* Per-Picard-iterate record of the last pdeode_step: CG iterations of each
+ * solve and (diffC, diffM) pairs (P:725-726); at most cap entries.  Returns
+ * the number of iterates in *count. */
+int pdeode_last_step_trace(pdeode_ctx *ctx, long long *nit_per_solve,
+                           double *diffs, int cap, int *count);
+
+/* Record (rho, dot, alfa, err2, normx) of every CG iteration of subsequent
+ * solves, up to cap iterations per solve (0 disables). */
+int pdeode_cg_trace_enable(pdeode_ctx *ctx, int cap);
+/* Fetch the trace of the most recent solve: 5 doubles per iteration. */
+int pdeode_cg_trace_get(pdeode_ctx *ctx, double *out, int cap, int *count);
+
+/* Device arrays, for parity tests: which = PDEODE_ARR_*; out = nrows*col. */
+#define PDEODE_ARR_M     0
+#define PDEODE_ARR_C     1
+#define PDEODE_ARR_MNEW  2   /* CG solution / next warm start (P:623) */
+#define PDEODE_ARR_D     3   /* D(Mprev) (P:544-546) */
+#define PDEODE_ARR_AC    4   /* centre diagonal (P:554-585) */
+#define PDEODE_ARR_R     5
+#define PDEODE_ARR_P     6
+#define PDEODE_ARR_Q     7
+int pdeode_debug_get_array(pdeode_ctx *ctx, int which, double *out);
+
+/* Kernels launched by this context so far. */
+int pdeode_launch_count(const pdeode_ctx *ctx, long long *launches);
+
+/* Time one kernel of the path in isolation on the context's current arrays:
+ * `reps` back-to-back launches bracketed by CUDA events on the context's
+ * stream; *ms_per_launch = elapsed / reps.  The arrays are scratch afterwards:
+ * call pdeode_set_state before stepping again. */
+#define PDEODE_KERNEL_CG_SPMV    0  /* p = r + beta p; q = A p; p.q, p.p */
+#define PDEODE_KERNEL_CG_UPDATE  1  /* x += alfa p; r -= alfa q; r.r, x.x */
+#define PDEODE_KERNEL_INIT       2  /* centre diagonal + r = b - A x0 */
+#define PDEODE_KERNEL_SOLVEC     3  /* C update + Picard residuals */
+#define PDEODE_KERNEL_DIFFCOEF   4  /* D(M) */
+int pdeode_time_kernel(pdeode_ctx *ctx, int kernel, int reps,
+                       float *ms_per_launch);
+
+/* Algorithmic bytes per grid cell moved by one launch of `kernel`. */
+int pdeode_kernel_bytes_per_cell(int kernel);
+
+const char *pdeode_strerror(int code);
+/* Text of the last CUDA / NCCL failure on this context ("" if none). */
+const char *pdeode_last_error(const pdeode_ctx *ctx);
+const char *pdeode_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -394,7 +394,7 @@ void oracle_get_mnew(const oracle_state *s, double *Mnew)
 
 void oracle_set_maxit(oracle_state *s, long long maxit)
 {
-    s->maxit = (maxit > 0) ? maxit : 100LL * (long long)s->n;
+    s->maxit = (maxit >= 0) ? maxit : 100LL * (long long)s->n;
 }
 
 /* P:700-742 */

@@ -90,7 +90,7 @@ void oracle_set_state(oracle_state *s, const double *M, const double *C);
 void oracle_get_state(const oracle_state *s, double *M, double *C);
 /* Mnew as left by the last solve (the next warm start). */
 void oracle_get_mnew(const oracle_state *s, double *Mnew);
-/* Override the CG iteration cap (default 100*n, P:707).  <=0 restores it. */
+/* Override the CG iteration cap (default 100*n, P:707).  <0 restores it. */
 void oracle_set_maxit(oracle_state *s, long long maxit);
 
 /* One pass of P:700-742.  Returns 0, or 1 when countIters exceeded 10000

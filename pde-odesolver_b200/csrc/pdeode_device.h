@@ -1,0 +1,142 @@
+// pdeode_device.h -- types shared by the kernels and the engine.
+//
+// Device layout (all arrays identical in shape):
+//   a slab of `rows` grid rows is stored with row pitch P (col rounded up to
+//   16 doubles = 128 B), one ghost row above and one below, and a 16-double
+//   guard at both ends, so that every 5-point neighbour of every cell --
+//   including (row -1, col -1) -- is a legal, finite address.  Pad columns
+//   [col, P) and unused ghost rows are kept at zero.  Array pointers handed
+//   to kernels point at (row 0, col 0).
+#pragma once
+#include <cuda_runtime.h>
+
+namespace pdeode {
+
+struct GridDesc {
+    int rows;        // local rows of this slab
+    int col;         // real columns
+    int P;           // row pitch in doubles
+    int row0;        // global index of local row 0
+    int grow;        // global row count
+    double n_glob;   // (double)(grow*col): divisor of CG:57,87 / P:789,961
+};
+
+// Numerical parameters in the form the kernels use them.
+struct NumParams {
+    double delta, nu, kappa, gama, tDel;
+    double h;        // (xCof*0.5), xCof = 1/(xDel*xDel)   (P:537,553)
+    double inv_dt;   // (1/tDel)                            (P:585)
+    double aux;      // tDel*0.5*gama                       (P:499)
+    double tol2;     // e2                                  (CG:40)
+    int alpha, beta, dSelect, fSelect, gSelect;
+};
+
+// Scalars of one CG solve / Picard iterate; lives in device memory.
+struct DevScal {
+    // CG state (CG:33)
+    double rho, rho_old, alfa;
+    double pq, pp;       // dotProd(p,q) (CG:76), sum(p*p) (CG:87)
+    double xx;           // sum(sol*sol) before this iteration's update (CG:57)
+    double err2, normx;
+    long long nit;       // CG:55
+    long long maxit;     // CG:40
+    int stop;            // stopcrit (CG:53,88,90)
+    int done;            // stop != 0: the update of this iteration is the last
+    int finished;        // that last update has been applied
+    int pad0;
+    // Picard residuals (P:725-726) and field sums of the new iterate
+    double diffC, diffM;
+    // diagnostics (P:772-791, P:978-1004)
+    double sumM, sumC;
+    double peak_val;
+    long long peak_idx;  // global cell index of the last maximal cell, -1 none
+    int intfac_row;      // last global row with M > 0.1, -1 none
+    int pad1;
+    // raw (rank-local) sums awaiting a cross-rank reduction
+    double part[4];
+    // per-solve trace
+    int trace_cap, trace_len;
+    // tickets for the last-block-done reductions
+    unsigned int ticket[8];
+};
+
+struct HostStatus {           // written by the device into mapped host memory
+    volatile long long seq_done;   // (seq << 1) | finished
+    volatile long long nit;
+    volatile long long seq_picard; // seq of the last completed solveC_diff
+    volatile double diffC, diffM;
+};
+
+enum { TICKET_STENCIL = 0, TICKET_UPDATE = 1, TICKET_SOLVEC = 2, TICKET_MASS = 3 };
+
+// Arguments of the 5-point marching kernel.
+struct StencilArgs {
+    GridDesc g;
+    NumParams np;
+    DevScal *S;
+    double *partials;      // [2][maxblocks]
+    HostStatus *hs;        // may be null
+    double *trace;         // may be null; 5 doubles per CG iteration
+    // INIT: x0 -> (ac, r, x);   CG: (r, p) -> (p, q)
+    const double *x0, *d, *Cc, *Mprev;
+    double *ac, *r, *x, *p, *q;
+    int TR;                // rows marched per CTA
+    int fuse_scalars;      // 1: last block turns sums into alfa/stop (single rank)
+    int write_ghost_top, write_ghost_bot; // maintain p ghost rows (multi rank)
+    long long seq;
+};
+
+struct UpdateArgs {
+    GridDesc g;
+    DevScal *S;
+    double *partials;
+    HostStatus *hs;
+    double *x, *r;
+    const double *p, *q;
+    long long n2;          // number of double2 elements to stream (rows*P/2)
+    int fuse_scalars;
+    long long seq;
+};
+
+struct SolveCArgs {
+    GridDesc g;
+    NumParams np;
+    DevScal *S;
+    double *partials;
+    HostStatus *hs;
+    const double *Mprev, *Mnew, *Cprev, *Ccur, *Mcur;
+    double *Cnew;
+    long long n2;
+    int fuse_scalars;
+    long long seq;
+};
+
+struct MassArgs {
+    GridDesc g;
+    DevScal *S;
+    double *partials;      // [4][maxblocks] + index arrays behind it
+    const double *M, *C;
+    long long n2;
+};
+
+// launchers (pdeode_kernels.cu)
+cudaError_t launch_diffcoef(const GridDesc &g, const NumParams &np, const double *M,
+                            double *d, cudaStream_t st);
+cudaError_t launch_stencil_init(const StencilArgs &a, cudaStream_t st);
+cudaError_t launch_stencil_cg(const StencilArgs &a, cudaStream_t st);
+cudaError_t launch_update(const UpdateArgs &a, cudaStream_t st);
+cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st);
+cudaError_t launch_mass(const MassArgs &a, cudaStream_t st);
+// scalar steps for the multi-rank path (sums already all-reduced into S->part)
+cudaError_t launch_scal_after_init(DevScal *S, cudaStream_t st);
+cudaError_t launch_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace,
+                                   HostStatus *hs, long long seq, cudaStream_t st);
+cudaError_t launch_scal_after_update(DevScal *S, HostStatus *hs, long long seq,
+                                     cudaStream_t st);
+cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq,
+                                     cudaStream_t st);
+int stencil_max_blocks(const GridDesc &g, int TR);
+int stream_blocks();
+void kernel_config_from_env();
+
+}  // namespace pdeode

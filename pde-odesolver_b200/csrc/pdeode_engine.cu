@@ -1,0 +1,726 @@
+// pdeode_engine.cu -- context, launch logic and the C ABI of libpdeode_b200.so
+// (include/pdeode_b200.h).  Host-driven engine: the Picard loop and the CG
+// loop run as kernel sequences on one stream; the device decides convergence
+// (stop test of CG:88-90, residuals of P:725-726) and the host reads one
+// small scalar record per chunk of CG iterations / per Picard iterate.
+//
+// There is no CPU fallback: without a CUDA device every entry point that
+// would compute returns PDEODE_ERR_NODEVICE.
+#include "../../include/pdeode_b200.h"
+#include "nccl_dyn.h"
+#include "pdeode_device.h"
+
+#include <algorithm>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+using namespace pdeode;
+
+namespace {
+
+constexpr int GUARD = 16;          // doubles in front of / behind every array
+constexpr int MAX_PICARD_TRACE = 64;
+constexpr int PICARD_CAP = 10000;  // P:732
+
+struct Snapshot { DevScal s; };
+
+}  // namespace
+
+struct pdeode_ctx {
+    int device = 0;
+    int rank = 0, nranks = 1;
+    GridDesc g{};
+    NumParams np{};
+    pdeode_params params{};
+    long long n_local = 0;        // rows * col
+    size_t arr_doubles = 0;       // allocation size of one array
+    long long maxit = 0, maxit_default = 0;
+
+    // field buffers: three M, three C (prev / current / new rotate), work arrays
+    double *base[11] = {nullptr};
+    double *Mb[3] = {nullptr}, *Cb[3] = {nullptr};
+    int iM = 0, iMprev = 0, iC = 0, iCprev = 0;
+    int iMnew = 1;                // buffer holding the last CG solution
+    double *d = nullptr, *ac = nullptr, *r = nullptr, *p = nullptr, *q = nullptr;
+    bool warm = false;            // false until the first solve: x0 = 0 (D8)
+
+    DevScal *S = nullptr;
+    double *partials = nullptr;
+    int max_blocks = 0;
+    double *trace = nullptr;
+    int trace_cap = 0;
+    double *gather = nullptr;     // multi-rank diagnostics
+    Snapshot *snap = nullptr;     // pinned, 2 slots
+    cudaEvent_t ev[2] = {nullptr, nullptr};
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    ncclComm_t comm = nullptr;
+
+    int TR = 16;
+    int pred[MAX_PICARD_TRACE];
+    long long seq = 0;
+    long long launches = 0;
+    bool mass_valid = false;
+
+    // last step trace
+    long long nit_trace[MAX_PICARD_TRACE];
+    double diff_trace[2 * MAX_PICARD_TRACE];
+    int trace_count = 0;
+
+    std::string err;
+};
+
+namespace {
+
+const char *const kVersion = "pdeode_b200 0.1 (sm_100a, fp64)";
+
+int fail_cuda(pdeode_ctx *c, cudaError_t e, const char *what) {
+    if (c) {
+        char buf[256];
+        snprintf(buf, sizeof buf, "%s: %s", what, cudaGetErrorString(e));
+        c->err = buf;
+    }
+    return (e == cudaErrorNoDevice || e == cudaErrorInsufficientDriver) ? PDEODE_ERR_NODEVICE
+                                                                      : PDEODE_ERR_CUDA;
+}
+
+int fail_nccl(pdeode_ctx *c, int e, const char *what) {
+    char buf[256];
+    const char *s = (nccl().GetErrorString) ? nccl().GetErrorString(e) : "?";
+    snprintf(buf, sizeof buf, "%s: nccl error %d (%s)", what, e, s);
+    c->err = buf;
+    return PDEODE_ERR_NCCL;
+}
+
+#define CK(call)                                                      \
+    do {                                                              \
+        cudaError_t e_ = (call);                                      \
+        if (e_ != cudaSuccess) return fail_cuda(c, e_, #call);        \
+    } while (0)
+#define NK(call)                                                      \
+    do {                                                              \
+        int e_ = (call);                                              \
+        if (e_ != NCCL_SUCCESS) return fail_nccl(c, e_, #call);       \
+    } while (0)
+
+inline bool multi(const pdeode_ctx *c) { return c->nranks > 1; }
+
+// ghost-row exchange with the slabs above and below (one row each way)
+int halo_exchange(pdeode_ctx *c, double *X) {
+    if (!multi(c)) return PDEODE_OK;
+    const size_t P = (size_t)c->g.P;
+    NK(nccl().GroupStart());
+    if (c->rank > 0) {
+        NK(nccl().Send(X, P, NCCL_DOUBLE, c->rank - 1, c->comm, c->stream));
+        NK(nccl().Recv(X - P, P, NCCL_DOUBLE, c->rank - 1, c->comm, c->stream));
+    }
+    if (c->rank < c->nranks - 1) {
+        NK(nccl().Send(X + (size_t)(c->g.rows - 1) * P, P, NCCL_DOUBLE, c->rank + 1, c->comm,
+                       c->stream));
+        NK(nccl().Recv(X + (size_t)c->g.rows * P, P, NCCL_DOUBLE, c->rank + 1, c->comm,
+                       c->stream));
+    }
+    NK(nccl().GroupEnd());
+    return PDEODE_OK;
+}
+
+int allreduce_part(pdeode_ctx *c, int count) {
+    NK(nccl().AllReduce(c->S->part, c->S->part, (size_t)count, NCCL_DOUBLE, NCCL_SUM, c->comm,
+                        c->stream));
+    return PDEODE_OK;
+}
+
+int snapshot(pdeode_ctx *c, int slot) {
+    CK(cudaMemcpyAsync(&c->snap[slot].s, c->S, sizeof(DevScal), cudaMemcpyDeviceToHost,
+                       c->stream));
+    CK(cudaEventRecord(c->ev[slot], c->stream));
+    return PDEODE_OK;
+}
+
+int wait_snapshot(pdeode_ctx *c, int slot) {
+    CK(cudaEventSynchronize(c->ev[slot]));
+    return PDEODE_OK;
+}
+
+StencilArgs stencil_args(pdeode_ctx *c) {
+    StencilArgs a{};
+    a.g = c->g; a.np = c->np; a.S = c->S; a.partials = c->partials;
+    a.hs = nullptr; a.trace = c->trace_cap > 0 ? c->trace : nullptr;
+    a.d = c->d; a.ac = c->ac; a.r = c->r; a.p = c->p; a.q = c->q;
+    a.TR = c->TR;
+    a.fuse_scalars = multi(c) ? 0 : 1;
+    a.write_ghost_top = multi(c) && c->rank > 0;
+    a.write_ghost_bot = multi(c) && c->rank < c->nranks - 1;
+    a.seq = c->seq;
+    return a;
+}
+
+// one CG iteration: CG:55-90
+int cg_iteration(pdeode_ctx *c, double *x) {
+    StencilArgs a = stencil_args(c);
+    CK(launch_stencil_cg(a, c->stream));
+    c->launches++;
+    if (multi(c)) {
+        int rc = allreduce_part(c, 2);
+        if (rc) return rc;
+        CK(launch_scal_after_spmv(c->S, c->g, c->np.tol2, a.trace, nullptr, c->seq, c->stream));
+        c->launches++;
+    }
+    UpdateArgs u{};
+    u.g = c->g; u.S = c->S; u.partials = c->partials; u.hs = nullptr;
+    u.x = x; u.r = c->r; u.p = c->p; u.q = c->q;
+    u.n2 = (long long)c->g.rows * c->g.P / 2;
+    u.fuse_scalars = multi(c) ? 0 : 1;
+    u.seq = c->seq;
+    CK(launch_update(u, c->stream));
+    c->launches++;
+    if (multi(c)) {
+        int rc = allreduce_part(c, 2);
+        if (rc) return rc;
+        CK(launch_scal_after_update(c->S, nullptr, c->seq, c->stream));
+        c->launches++;
+        rc = halo_exchange(c, c->r);
+        if (rc) return rc;
+    }
+    return PDEODE_OK;
+}
+
+// GenMatrixM's centre diagonal + solveLSDIAG (P:712-714): x0 -> x.
+int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *nit_out,
+          int *stop_out) {
+    c->seq++;
+    if (multi(c)) {
+        int rc = halo_exchange(c, const_cast<double *>(x0));
+        if (rc) return rc;
+    }
+    StencilArgs a = stencil_args(c);
+    a.x0 = x0; a.x = x; a.Cc = c->Cb[c->iC]; a.Mprev = c->Mb[c->iMprev];
+    CK(launch_stencil_init(a, c->stream));
+    c->launches++;
+    if (multi(c)) {
+        int rc = allreduce_part(c, 2);
+        if (rc) return rc;
+        CK(launch_scal_after_init(c->S, c->stream));
+        c->launches++;
+        rc = halo_exchange(c, c->r);
+        if (rc) return rc;
+    }
+
+    // CG iterations in chunks; the device flags convergence, later launches
+    // of a finished solve return at once.
+    const int pred = std::max(1, c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)]);
+    long long launched = 0;
+    int slot = 0;
+    int chunk = (int)std::min<long long>(pred, 2048);
+    bool have_pending = false;
+    int pending_slot = 0;
+    for (;;) {
+        for (int k = 0; k < chunk; ++k) {
+            int rc = cg_iteration(c, x);
+            if (rc) return rc;
+        }
+        launched += chunk;
+        int rc = snapshot(c, slot);
+        if (rc) return rc;
+        if (have_pending) {
+            rc = wait_snapshot(c, pending_slot);
+            if (rc) return rc;
+            if (c->snap[pending_slot].s.finished) {
+                // the chunk just queued is all no-ops; its snapshot is the final state
+                rc = wait_snapshot(c, slot);
+                if (rc) return rc;
+                break;
+            }
+        }
+        // run ahead by one more chunk only when a solve is long enough to hide it
+        const long long seen = have_pending ? c->snap[pending_slot].s.nit : 0;
+        if (pred > 8 || have_pending) {
+            have_pending = true;
+            pending_slot = slot;
+            slot ^= 1;
+            chunk = (int)std::min<long long>(std::max<long long>(2, std::max<long long>(seen, launched) / 8), 1024);
+            continue;
+        }
+        rc = wait_snapshot(c, slot);
+        if (rc) return rc;
+        if (c->snap[slot].s.finished) break;
+        chunk = (int)std::min<long long>(std::max<long long>(2, launched / 2), 1024);
+    }
+    const DevScal &fin = c->snap[slot].s;
+    *nit_out = fin.nit;
+    *stop_out = fin.stop;
+    c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)] = (int)std::min<long long>(fin.nit, 1 << 20);
+    return PDEODE_OK;
+}
+
+int upload(pdeode_ctx *c, double *dst, const double *src) {
+    CK(cudaMemcpy2DAsync(dst, (size_t)c->g.P * sizeof(double), src,
+                         (size_t)c->g.col * sizeof(double), (size_t)c->g.col * sizeof(double),
+                         (size_t)c->g.rows, cudaMemcpyHostToDevice, c->stream));
+    return PDEODE_OK;
+}
+
+int download(pdeode_ctx *c, double *dst, const double *src) {
+    CK(cudaMemcpy2DAsync(dst, (size_t)c->g.col * sizeof(double), src,
+                         (size_t)c->g.P * sizeof(double), (size_t)c->g.col * sizeof(double),
+                         (size_t)c->g.rows, cudaMemcpyDeviceToHost, c->stream));
+    return PDEODE_OK;
+}
+
+int zero_array(pdeode_ctx *c, int k) {
+    CK(cudaMemsetAsync(c->base[k], 0, c->arr_doubles * sizeof(double), c->stream));
+    return PDEODE_OK;
+}
+
+int run_mass(pdeode_ctx *c) {
+    if (c->mass_valid) return PDEODE_OK;
+    MassArgs m{};
+    m.g = c->g; m.S = c->S; m.partials = c->partials;
+    m.M = c->Mb[c->iM]; m.C = c->Cb[c->iC];
+    m.n2 = (long long)c->g.rows * c->g.P / 2;
+    CK(launch_mass(m, c->stream));
+    c->launches++;
+    int rc = snapshot(c, 0);
+    if (rc) return rc;
+    rc = wait_snapshot(c, 0);
+    if (rc) return rc;
+    if (multi(c)) {
+        // gather (sumM, sumC, peak_val, peak_idx, intfac_row) of every rank
+        double loc[8] = {c->snap[0].s.sumM, c->snap[0].s.sumC, c->snap[0].s.peak_val,
+                         (double)c->snap[0].s.peak_idx, (double)c->snap[0].s.intfac_row, 0, 0, 0};
+        CK(cudaMemcpyAsync(c->gather + 8 * c->rank, loc, sizeof loc, cudaMemcpyHostToDevice,
+                           c->stream));
+        NK(nccl().AllGather(c->gather + 8 * c->rank, c->gather, 8, NCCL_DOUBLE, c->comm,
+                            c->stream));
+        std::vector<double> all(8 * (size_t)c->nranks);
+        CK(cudaMemcpyAsync(all.data(), c->gather, all.size() * sizeof(double),
+                           cudaMemcpyDeviceToHost, c->stream));
+        CK(cudaStreamSynchronize(c->stream));
+        DevScal &s = c->snap[0].s;
+        s.sumM = s.sumC = 0.0; s.peak_val = -1.0; s.peak_idx = -1; s.intfac_row = -1;
+        for (int r = 0; r < c->nranks; ++r) {      // rank order = row order
+            const double *v = &all[8 * (size_t)r];
+            s.sumM += v[0]; s.sumC += v[1];
+            if ((long long)v[3] >= 0 && v[2] >= s.peak_val) { s.peak_val = v[2]; s.peak_idx = (long long)v[3]; }
+            if ((int)v[4] > s.intfac_row) s.intfac_row = (int)v[4];
+        }
+    }
+    c->mass_valid = true;
+    return PDEODE_OK;
+}
+
+void set_numparams(pdeode_ctx *c, const pdeode_params *p) {
+    NumParams &n = c->np;
+    n.delta = p->delta; n.nu = p->nu; n.kappa = p->kappa; n.gama = p->gama; n.tDel = p->tDel;
+    const double xCof = 1.0 / (p->xDel * p->xDel);      // P:537
+    n.h = xCof * 0.5;                                   // P:553 (left to right)
+    n.inv_dt = 1.0 / p->tDel;                           // P:585
+    n.aux = p->tDel * 0.5 * p->gama;                    // P:499
+    n.tol2 = p->e2;                                     // CG:40
+    n.alpha = p->alpha; n.beta = p->beta;
+    n.dSelect = p->dSelect; n.fSelect = p->fSelect; n.gSelect = p->gSelect;
+}
+
+int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int device, int rank,
+                int nranks, const void *id) {
+    if (!out) return PDEODE_ERR_ARG;
+    *out = nullptr;
+    if (!p || row < 3 || col < 2 || nranks < 1 || rank < 0 || rank >= nranks ||
+        row / nranks < 2 || (nranks > 1 && !id) || !(p->tDel > 0) || !(p->xDel > 0))
+        return PDEODE_ERR_ARG;
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0) return PDEODE_ERR_NODEVICE;
+    if (device < 0 || device >= ndev) return PDEODE_ERR_ARG;
+    pdeode_ctx *c = new (std::nothrow) pdeode_ctx();
+    if (!c) return PDEODE_ERR_NOMEM;
+    *out = c;   // returned even on failure so that pdeode_last_error works; destroy it
+    c->device = device; c->rank = rank; c->nranks = nranks; c->params = *p;
+    CK(cudaSetDevice(device));
+    kernel_config_from_env();
+    if (const char *t = getenv("PDEODE_TR")) { int v = atoi(t); if (v >= 1 && v <= 4096) c->TR = v; }
+
+    const int r0 = (int)((long long)rank * row / nranks);
+    const int r1 = (int)((long long)(rank + 1) * row / nranks);
+    c->g.rows = r1 - r0; c->g.col = col; c->g.P = (col + 15) / 16 * 16;
+    c->g.row0 = r0; c->g.grow = row;
+    c->g.n_glob = (double)((long long)row * col);
+    c->n_local = (long long)c->g.rows * col;
+    c->maxit_default = 100LL * row * col;               // P:707 (64-bit: SURVEY D9)
+    c->maxit = c->maxit_default;
+    set_numparams(c, p);
+    for (int k = 0; k < MAX_PICARD_TRACE; ++k) c->pred[k] = (k == 0) ? 8 : 1;
+
+    c->arr_doubles = (size_t)(c->g.rows + 2) * c->g.P + 2 * GUARD;
+    for (int k = 0; k < 11; ++k) {
+        cudaError_t me = cudaMalloc(&c->base[k], c->arr_doubles * sizeof(double));
+        if (me != cudaSuccess) {
+            fail_cuda(c, me, "cudaMalloc(field)");
+            return me == cudaErrorMemoryAllocation ? PDEODE_ERR_NOMEM : PDEODE_ERR_CUDA;
+        }
+        CK(cudaMemset(c->base[k], 0, c->arr_doubles * sizeof(double)));
+    }
+    auto origin = [&](int k) { return c->base[k] + GUARD + c->g.P; };
+    for (int k = 0; k < 3; ++k) { c->Mb[k] = origin(k); c->Cb[k] = origin(3 + k); }
+    c->d = origin(6); c->ac = origin(7); c->r = origin(8); c->p = origin(9); c->q = origin(10);
+
+    c->max_blocks = std::max(stencil_max_blocks(c->g, 1), std::max(stream_blocks(), 512));
+    // the marching kernel never launches more CTAs than stencil_max_blocks(g, TR)
+    c->max_blocks = std::max(stencil_max_blocks(c->g, c->TR), std::max(stream_blocks(), 512));
+    CK(cudaMalloc(&c->partials, sizeof(double) * 8 * (size_t)c->max_blocks));
+    CK(cudaMalloc(&c->S, sizeof(DevScal)));
+    CK(cudaMemset(c->S, 0, sizeof(DevScal)));
+    CK(cudaMallocHost(&c->snap, 2 * sizeof(Snapshot)));
+    memset(c->snap, 0, 2 * sizeof(Snapshot));
+    CK(cudaEventCreateWithFlags(&c->ev[0], cudaEventDisableTiming));
+    CK(cudaEventCreateWithFlags(&c->ev[1], cudaEventDisableTiming));
+    CK(cudaStreamCreateWithFlags(&c->own_stream, cudaStreamNonBlocking));
+    c->stream = c->own_stream;
+    CK(cudaMemcpy(&c->S->maxit, &c->maxit, sizeof(long long), cudaMemcpyHostToDevice));
+
+    if (nranks > 1) {
+        if (!nccl().ok) { c->err = "libnccl.so.2 not found"; return PDEODE_ERR_NCCL; }
+        ncclUniqueId uid;
+        memcpy(&uid, id, sizeof uid);
+        NK(nccl().CommInitRank(&c->comm, nranks, uid, rank));
+        CK(cudaMalloc(&c->gather, sizeof(double) * 8 * (size_t)nranks));
+    }
+    return PDEODE_OK;
+}
+
+}  // namespace
+
+// ======================================================================
+extern "C" {
+
+const char *pdeode_version(void) { return kVersion; }
+
+const char *pdeode_strerror(int code) {
+    switch (code & PDEODE_ERR_MASK) {
+    case PDEODE_OK: return (code & PDEODE_WARN_CG_CAP) ? "ok (a CG solve hit its iteration cap)" : "ok";
+    case PDEODE_ERR_CUDA: return "CUDA error";
+    case PDEODE_ERR_NCCL: return "NCCL error";
+    case PDEODE_ERR_ARG: return "invalid argument";
+    case PDEODE_ERR_PICARD_CAP: return "over 10000 Picard iterations in one timestep; solutions not converging";
+    case PDEODE_ERR_NOMEM: return "out of memory";
+    case PDEODE_ERR_NODEVICE: return "no CUDA device (this library has no CPU fallback)";
+    default: return "unknown error";
+    }
+}
+
+const char *pdeode_last_error(const pdeode_ctx *c) { return c ? c->err.c_str() : ""; }
+
+int pdeode_nccl_unique_id(void *id_out) {
+    if (!id_out) return PDEODE_ERR_ARG;
+    if (!nccl().ok) return PDEODE_ERR_NCCL;
+    ncclUniqueId uid;
+    if (nccl().GetUniqueId(&uid) != NCCL_SUCCESS) return PDEODE_ERR_NCCL;
+    memcpy(id_out, &uid, sizeof uid);
+    return PDEODE_OK;
+}
+
+int pdeode_create(pdeode_ctx **ctx, int row, int col, const pdeode_params *p, int device) {
+    return create_impl(ctx, row, col, p, device, 0, 1, nullptr);
+}
+
+int pdeode_create_dist(pdeode_ctx **ctx, int row, int col, const pdeode_params *p, int device,
+                       int rank, int nranks, const void *id) {
+    return create_impl(ctx, row, col, p, device, rank, nranks, id);
+}
+
+int pdeode_destroy(pdeode_ctx *c) {
+    if (!c) return PDEODE_OK;
+    cudaSetDevice(c->device);
+    if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->comm) nccl().CommDestroy(c->comm);
+    for (int k = 0; k < 11; ++k) if (c->base[k]) cudaFree(c->base[k]);
+    if (c->partials) cudaFree(c->partials);
+    if (c->S) cudaFree(c->S);
+    if (c->trace) cudaFree(c->trace);
+    if (c->gather) cudaFree(c->gather);
+    if (c->snap) cudaFreeHost(c->snap);
+    if (c->ev[0]) cudaEventDestroy(c->ev[0]);
+    if (c->ev[1]) cudaEventDestroy(c->ev[1]);
+    if (c->own_stream) cudaStreamDestroy(c->own_stream);
+    delete c;
+    return PDEODE_OK;
+}
+
+int pdeode_local_rows(const pdeode_ctx *c, int *row0, int *nrows) {
+    if (!c) return PDEODE_ERR_ARG;
+    if (row0) *row0 = c->g.row0;
+    if (nrows) *nrows = c->g.rows;
+    return PDEODE_OK;
+}
+
+int pdeode_set_stream(pdeode_ctx *c, void *cuda_stream) {
+    if (!c) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
+    return PDEODE_OK;
+}
+
+int pdeode_set_state(pdeode_ctx *c, const double *M, const double *C) {
+    if (!c || !M || !C) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->iM = c->iMprev = 0; c->iC = c->iCprev = 0; c->iMnew = 1;
+    int rc;
+    if ((rc = upload(c, c->Mb[0], M))) return rc;
+    if ((rc = upload(c, c->Cb[0], C))) return rc;
+    if ((rc = zero_array(c, 1))) return rc;     // Mnew := 0, the first warm start (D8)
+    c->warm = false;
+    c->mass_valid = false;
+    CK(cudaStreamSynchronize(c->stream));
+    return PDEODE_OK;
+}
+
+int pdeode_get_state(pdeode_ctx *c, double *M, double *C) {
+    if (!c || !M || !C) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    if ((rc = download(c, M, c->Mb[c->iM]))) return rc;
+    if ((rc = download(c, C, c->Cb[c->iC]))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return PDEODE_OK;
+}
+
+// P:700-742
+int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nitMax) {
+    if (!c) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int rc;
+    int warn = 0;
+    // Cprev = C ; Mprev = M (P:703-704): the current buffers become the frozen ones
+    c->iMprev = c->iM; c->iCprev = c->iC;
+    // d = D(Mprev) (P:544-546); fixed over the Picard loop because GenMatrixM
+    // is always handed Mprev (P:712)
+    CK(launch_diffcoef(c->g, c->np, c->Mb[c->iMprev], c->d, c->stream));
+    c->launches++;
+    if ((rc = halo_exchange(c, c->d))) return rc;
+
+    double diffC = 1.0, diffM = 1.0;                 // P:700-701
+    int count = 0;                                   // P:702
+    long long sum = 0, mx = 0;
+    c->trace_count = 0;
+    while (diffC + diffM > c->params.eSoln) {        // P:706
+        // target buffer of this solve: neither Mprev nor the current iterate
+        int inew = 0;
+        while (inew == c->iMprev || inew == c->iM) inew++;
+        if (!c->warm) inew = c->iMnew;               // the zeroed buffer (first solve ever)
+        const double *x0 = c->warm ? c->Mb[c->iM] : c->Mb[inew];
+        long long nit = 0; int stop = 0;
+        if ((rc = solve(c, x0, c->Mb[inew], count, &nit, &stop))) return rc;
+        c->warm = true;
+        c->iMnew = inew;
+        if (stop == -1 || stop == -101) warn = PDEODE_WARN_CG_CAP;
+
+        int icnew = 0;
+        while (icnew == c->iCprev || icnew == c->iC) icnew++;
+        SolveCArgs s{};
+        s.g = c->g; s.np = c->np; s.S = c->S; s.partials = c->partials; s.hs = nullptr;
+        s.Mprev = c->Mb[c->iMprev]; s.Mnew = c->Mb[inew]; s.Cprev = c->Cb[c->iCprev];
+        s.Ccur = c->Cb[c->iC]; s.Mcur = c->Mb[c->iM]; s.Cnew = c->Cb[icnew];
+        s.n2 = (long long)c->g.rows * c->g.P / 2;
+        s.fuse_scalars = multi(c) ? 0 : 1;
+        s.seq = c->seq;
+        CK(launch_solvec(s, c->stream));             // P:717, P:725-726
+        c->launches++;
+        if (multi(c)) {
+            if ((rc = allreduce_part(c, 2))) return rc;
+            CK(launch_scal_after_solvec(c->S, c->g, nullptr, c->seq, c->stream));
+            c->launches++;
+        }
+        if ((rc = snapshot(c, 0))) return rc;
+        if ((rc = wait_snapshot(c, 0))) return rc;
+        diffC = c->snap[0].s.diffC;
+        diffM = c->snap[0].s.diffM;
+
+        if (nit > mx) mx = nit;                      // P:722
+        sum += nit;                                  // P:723
+        c->iC = icnew;                               // C = Cnew (P:728)
+        c->iM = inew;                                // M = Mnew (P:729)
+        if (count < MAX_PICARD_TRACE) {
+            c->nit_trace[count] = nit;
+            c->diff_trace[2 * count] = diffC;
+            c->diff_trace[2 * count + 1] = diffM;
+            c->trace_count = count + 1;
+        }
+        count++;                                     // P:730
+        c->mass_valid = false;
+        if (count > PICARD_CAP) {                    // P:732
+            if (countIters) *countIters = count;
+            if (nitSum) *nitSum = sum;
+            if (nitMax) *nitMax = mx;
+            return PDEODE_ERR_PICARD_CAP;
+        }
+    }
+    if (countIters) *countIters = count;
+    if (nitSum) *nitSum = sum;
+    if (nitMax) *nitMax = mx;
+    return PDEODE_OK | warn;
+}
+
+int pdeode_mass(pdeode_ctx *c, double *meanM, double *meanC) {
+    if (!c) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int rc = run_mass(c);
+    if (rc) return rc;
+    if (meanM) *meanM = c->snap[0].s.sumM / c->g.n_glob;     // P:789
+    if (meanC) *meanC = c->snap[0].s.sumC / c->g.n_glob;
+    return PDEODE_OK;
+}
+
+int pdeode_peak(pdeode_ctx *c, double *peak, double *height, double *intfac) {
+    if (!c) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int rc = run_mass(c);
+    if (rc) return rc;
+    const DevScal &s = c->snap[0].s;
+    const double denom = (double)(c->g.grow - 1);            // P:990
+    if (s.peak_idx >= 0) {
+        if (peak) *peak = (double)(s.peak_idx / c->g.col) / denom;
+        if (height) *height = s.peak_val;
+    } else if (height) {
+        *height = 0.0;                                       // hei = 0 (P:988,1002)
+    }
+    if (s.intfac_row >= 0 && intfac) *intfac = (double)s.intfac_row / denom;
+    return PDEODE_OK;
+}
+
+int pdeode_set_maxit(pdeode_ctx *c, long long maxit) {
+    if (!c) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->maxit = maxit >= 0 ? maxit : c->maxit_default;
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaMemcpy(&c->S->maxit, &c->maxit, sizeof(long long), cudaMemcpyHostToDevice));
+    return PDEODE_OK;
+}
+
+int pdeode_last_step_trace(pdeode_ctx *c, long long *nit_per_solve, double *diffs, int cap,
+                           int *count) {
+    if (!c) return PDEODE_ERR_ARG;
+    const int k = std::min(cap, c->trace_count);
+    for (int i = 0; i < k; ++i) {
+        if (nit_per_solve) nit_per_solve[i] = c->nit_trace[i];
+        if (diffs) { diffs[2 * i] = c->diff_trace[2 * i]; diffs[2 * i + 1] = c->diff_trace[2 * i + 1]; }
+    }
+    if (count) *count = c->trace_count;
+    return PDEODE_OK;
+}
+
+int pdeode_cg_trace_enable(pdeode_ctx *c, int cap) {
+    if (!c || cap < 0) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    if (c->trace) { cudaFree(c->trace); c->trace = nullptr; }
+    c->trace_cap = cap;
+    if (cap > 0) CK(cudaMalloc(&c->trace, sizeof(double) * 5 * (size_t)cap));
+    CK(cudaMemcpy(&c->S->trace_cap, &cap, sizeof(int), cudaMemcpyHostToDevice));
+    return PDEODE_OK;
+}
+
+int pdeode_cg_trace_get(pdeode_ctx *c, double *out, int cap, int *count) {
+    if (!c || !out) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    int len = 0;
+    CK(cudaMemcpy(&len, &c->S->trace_len, sizeof(int), cudaMemcpyDeviceToHost));
+    const int k = std::min(std::min(len, cap), c->trace_cap);
+    if (k > 0) CK(cudaMemcpy(out, c->trace, sizeof(double) * 5 * (size_t)k, cudaMemcpyDeviceToHost));
+    if (count) *count = len;
+    return PDEODE_OK;
+}
+
+int pdeode_debug_get_array(pdeode_ctx *c, int which, double *out) {
+    if (!c || !out) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    const double *src = nullptr;
+    switch (which) {
+    case PDEODE_ARR_M: src = c->Mb[c->iM]; break;
+    case PDEODE_ARR_C: src = c->Cb[c->iC]; break;
+    case PDEODE_ARR_MNEW: src = c->Mb[c->iMnew]; break;
+    case PDEODE_ARR_D: src = c->d; break;
+    case PDEODE_ARR_AC: src = c->ac; break;
+    case PDEODE_ARR_R: src = c->r; break;
+    case PDEODE_ARR_P: src = c->p; break;
+    case PDEODE_ARR_Q: src = c->q; break;
+    default: return PDEODE_ERR_ARG;
+    }
+    int rc = download(c, out, src);
+    if (rc) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return PDEODE_OK;
+}
+
+int pdeode_launch_count(const pdeode_ctx *c, long long *launches) {
+    if (!c || !launches) return PDEODE_ERR_ARG;
+    *launches = c->launches;
+    return PDEODE_OK;
+}
+
+int pdeode_kernel_bytes_per_cell(int kernel) {
+    switch (kernel) {
+    case PDEODE_KERNEL_CG_SPMV: return 48;    // R r,p,d,ac  W p,q
+    case PDEODE_KERNEL_CG_UPDATE: return 48;  // R x,p,q,r   W x,r
+    case PDEODE_KERNEL_INIT: return 56;       // R x0,d,C,Mprev  W ac,r,x
+    case PDEODE_KERNEL_SOLVEC: return 48;     // R Mprev,Mnew,Cprev,C,M  W Cnew
+    case PDEODE_KERNEL_DIFFCOEF: return 16;   // R Mprev  W d
+    default: return 0;
+    }
+}
+
+int pdeode_time_kernel(pdeode_ctx *c, int kernel, int reps, float *ms_per_launch) {
+    if (!c || reps < 1 || !ms_per_launch) return PDEODE_ERR_ARG;
+    if (multi(c)) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    // put the CG scalars into a neutral mid-solve state: beta = 0.5, alfa = 1e-3
+    DevScal s{};
+    CK(cudaMemcpy(&s, c->S, sizeof s, cudaMemcpyDeviceToHost));
+    s.rho = 1.0; s.rho_old = 2.0; s.alfa = 1e-3; s.nit = 1; s.done = 0; s.finished = 0;
+    s.maxit = c->maxit;
+    for (int k = 0; k < 8; ++k) s.ticket[k] = 0;
+    CK(cudaMemcpy(c->S, &s, sizeof s, cudaMemcpyHostToDevice));
+    cudaEvent_t e0, e1;
+    CK(cudaEventCreate(&e0));
+    CK(cudaEventCreate(&e1));
+    StencilArgs a = stencil_args(c);
+    a.fuse_scalars = 0;
+    a.x0 = c->Mb[c->iM]; a.x = c->Mb[(c->iM + 1) % 3]; a.Cc = c->Cb[c->iC]; a.Mprev = c->Mb[c->iM];
+    UpdateArgs u{};
+    u.g = c->g; u.S = c->S; u.partials = c->partials; u.x = c->Mb[(c->iM + 1) % 3]; u.r = c->r;
+    u.p = c->p; u.q = c->q; u.n2 = (long long)c->g.rows * c->g.P / 2; u.fuse_scalars = 0;
+    SolveCArgs sc{};
+    sc.g = c->g; sc.np = c->np; sc.S = c->S; sc.partials = c->partials;
+    sc.Mprev = c->Mb[c->iM]; sc.Mnew = c->Mb[(c->iM + 1) % 3]; sc.Cprev = c->Cb[c->iC];
+    sc.Ccur = c->Cb[c->iC]; sc.Mcur = c->Mb[c->iM]; sc.Cnew = c->Cb[(c->iC + 1) % 3];
+    sc.n2 = u.n2; sc.fuse_scalars = 0;
+    for (int it = -1; it < reps; ++it) {     // one untimed launch first
+        if (it == 0) CK(cudaEventRecord(e0, c->stream));
+        switch (kernel) {
+        case PDEODE_KERNEL_CG_SPMV: CK(launch_stencil_cg(a, c->stream)); break;
+        case PDEODE_KERNEL_CG_UPDATE: CK(launch_update(u, c->stream)); break;
+        case PDEODE_KERNEL_INIT: CK(launch_stencil_init(a, c->stream)); break;
+        case PDEODE_KERNEL_SOLVEC: CK(launch_solvec(sc, c->stream)); break;
+        case PDEODE_KERNEL_DIFFCOEF:
+            CK(launch_diffcoef(c->g, c->np, c->Mb[c->iM], c->d, c->stream)); break;
+        default: return PDEODE_ERR_ARG;
+        }
+        c->launches++;
+    }
+    CK(cudaEventRecord(e1, c->stream));
+    CK(cudaEventSynchronize(e1));
+    float ms = 0.f;
+    CK(cudaEventElapsedTime(&ms, e0, e1));
+    *ms_per_launch = ms / (float)reps;
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    c->mass_valid = false;
+    return PDEODE_OK;
+}
+
+}  // extern "C"

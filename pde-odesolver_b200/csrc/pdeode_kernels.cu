@@ -1,0 +1,651 @@
+// pdeode_kernels.cu -- fp64 sm_100a kernels of the implicit time step.
+//
+// Compiled with -fmad=false: the reference build (gfortran -O3 on baseline
+// x86-64, runAll.sh:6) has no fused multiply-add, so every product and sum
+// below rounds separately, in the order the cited reference line evaluates it.
+// Division and sqrt are IEEE-correct in CUDA fp64.  Element-wise results are
+// therefore bit-identical to the reference's; only the reductions (parallel
+// tree here, serial loop there) differ, at the 1e-16 level.
+//
+// Kernels (P: = PDE-ODEsolver.f90, CG: = CGdiag.f90 of the reference):
+//   k_diffcoef   d = D(Mprev)                                  P:544-546
+//   k_stencil<INIT>  centre diagonal, r = b - A x0, x = x0     P:551-586, CG:46-50
+//   k_stencil<CG>    p = r + beta p ; q = A p ; p.q ; p.p      CG:61-76,87  P:1087-1102
+//   k_update     x += alfa p ; r -= alfa q ; r.r ; x.x         CG:57,59,79-86
+//   k_solvec     C update + Picard residuals                   P:504-506, P:948-963
+//   k_mass       calcMass + calcPeakInterface                  P:772-791, P:978-1004
+// The 5-diagonal matrix is never stored: off-diagonals are rebuilt from
+// d = D(Mprev) in registers, the centre diagonal `ac` is stored once per
+// Picard iterate.
+#include "pdeode_device.h"
+
+#include <cstdlib>
+
+namespace pdeode {
+
+namespace {
+
+constexpr unsigned FULL = 0xffffffffu;
+
+int g_bs_stencil = 128;   // threads per CTA of the marching kernel
+int g_stream_ctas_per_sm = 8;
+int g_num_sms = 148;
+
+// ---------------------------------------------------------------- helpers
+
+__device__ __forceinline__ double2 ld2(const double *p) {
+    return *reinterpret_cast<const double2 *>(p);
+}
+__device__ __forceinline__ void st2(double *p, double2 v) {
+    *reinterpret_cast<double2 *>(p) = v;
+}
+
+// libgcc __powidf2: what gfortran emits for real**integer_variable (P:470-471)
+__device__ __forceinline__ double powi(double x, int m) {
+    unsigned int n = (m < 0) ? (0u - (unsigned int)m) : (unsigned int)m;
+    double y = (n & 1u) ? x : 1.0;
+    while (n >>= 1) {
+        x = x * x;
+        if (n & 1u) y *= x;
+    }
+    return (m < 0) ? 1.0 / y : y;
+}
+
+// P:464-472
+__device__ __forceinline__ double dfunc(double M, const NumParams &np) {
+    double d = 0.0;
+    if (np.dSelect == 1) d = np.delta;
+    else if (np.dSelect == 2) d = np.delta * powi(M, np.alpha);
+    else if (np.dSelect == 3) d = np.delta * powi(M, np.alpha) / powi(1.0 - M, np.beta);
+    return d;
+}
+
+// P:445-458
+__device__ __forceinline__ double ffunc(double M, double C, const NumParams &np) {
+    const double eps = C * 0.00000001;
+    switch (np.fSelect) {
+    case 1: return C / (np.kappa + C) - np.nu;
+    case 2: return C / (np.kappa + C);
+    case 3: return C / (np.kappa * M + C + eps) - np.nu;
+    case 4: return C / (np.kappa * M + C + eps);
+    case 5: return 1.0;
+    case 6: return C / (np.kappa + C) * (1.0 - M / (C + eps)) - np.nu;
+    default: return 0.0;
+    }
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+    return v;
+}
+
+// Sum of (a, b) over the block; result valid in thread 0.  sm: 64 doubles.
+__device__ __forceinline__ void block_sum2(double &a, double &b, double *sm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a);
+    b = warp_sum(b);
+    if (lane == 0) { sm[w] = a; sm[32 + w] = b; }
+    __syncthreads();
+    if (w == 0) {
+        a = (lane < nw) ? sm[lane] : 0.0;
+        b = (lane < nw) ? sm[32 + lane] : 0.0;
+        a = warp_sum(a);
+        b = warp_sum(b);
+    }
+    __syncthreads();
+}
+
+// Two-stage deterministic reduction: every CTA stores its partial pair, the
+// CTA that draws the last ticket adds all partials in a fixed order.  Returns
+// true in thread 0 of that last CTA with (a, b) = grid totals.
+__device__ __forceinline__ bool grid_sum2(double &a, double &b, double *partials, int nb,
+                                          int bid, unsigned int *ticket, double *sm) {
+    __shared__ int s_last;
+    block_sum2(a, b, sm);
+    if (threadIdx.x == 0) {
+        partials[bid] = a;
+        partials[nb + bid] = b;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last = (t == (unsigned int)(nb - 1));
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    double x = 0.0, y = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        x += __ldcg(partials + i);
+        y += __ldcg(partials + nb + i);
+    }
+    block_sum2(x, y, sm);
+    a = x; b = y;
+    if (threadIdx.x == 0) *ticket = 0u;
+    return threadIdx.x == 0;
+}
+
+// ---------------------------------------------------------------- scalars
+
+// CG:53 (nit = 0, stopcrit = 0) with rho / sum(sol*sol) of the start vector
+__device__ __forceinline__ void scal_after_init(DevScal *S, double rr, double xx) {
+    S->rho = rr;          // dotProd(r,r) seen by iteration 1 (CG:59)
+    S->rho_old = 0.0;     // CG:44
+    S->xx = xx;           // sum(sol*sol) seen by iteration 1 (CG:57)
+    S->nit = 0; S->stop = 0; S->done = 0; S->finished = 0;
+    S->trace_len = 0;
+}
+
+// CG:55,77,87-90
+__device__ __forceinline__ void scal_after_spmv(DevScal *S, double pq, double pp,
+                                                double n_glob, double tol2, double *trace,
+                                                HostStatus *hs) {
+    const long long nit = S->nit + 1;                      // CG:55
+    const double alfa = S->rho / pq;                       // CG:77
+    const double err2 = fabs(alfa) * sqrt(pp) / n_glob;    // CG:87
+    const double normx = sqrt(S->xx) / n_glob;             // CG:57
+    int stop = 0;
+    if (nit > S->maxit) stop = -1;                         // CG:88
+    if (err2 < tol2 * normx) stop = stop - 100;            // CG:90
+    if (trace && nit <= (long long)S->trace_cap) {
+        double *t = trace + 5 * (nit - 1);
+        t[0] = S->rho; t[1] = pq; t[2] = alfa; t[3] = err2; t[4] = normx;
+        S->trace_len = (int)nit;
+    }
+    S->pq = pq; S->pp = pp; S->alfa = alfa; S->err2 = err2; S->normx = normx;
+    S->nit = nit; S->stop = stop; S->done = (stop != 0);
+    if (hs) hs->nit = nit;
+}
+
+__device__ __forceinline__ void scal_after_update(DevScal *S, double rr, double xx,
+                                                  HostStatus *hs, long long seq) {
+    S->rho_old = S->rho;  // CG:56
+    S->rho = rr;          // CG:59 of the next iteration
+    S->xx = xx;           // CG:57 of the next iteration
+    S->finished = S->done;
+    if (hs) {
+        __threadfence_system();
+        hs->seq_done = (seq << 1) | (long long)S->finished;
+    }
+}
+
+// P:961
+__device__ __forceinline__ void scal_after_solvec(DevScal *S, double dC, double dM,
+                                                  double n_glob, HostStatus *hs,
+                                                  long long seq) {
+    S->diffC = dC / n_glob;
+    S->diffM = dM / n_glob;
+    if (hs) {
+        hs->diffC = S->diffC;
+        hs->diffM = S->diffM;
+        __threadfence_system();
+        hs->seq_picard = seq;
+    }
+}
+
+__global__ void k_scal_after_init(DevScal *S) { scal_after_init(S, S->part[0], S->part[1]); }
+__global__ void k_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace,
+                                  HostStatus *hs) {
+    if (S->done) return;
+    scal_after_spmv(S, S->part[0], S->part[1], g.n_glob, tol2, trace, hs);
+}
+__global__ void k_scal_after_update(DevScal *S, HostStatus *hs, long long seq) {
+    if (S->finished) return;
+    scal_after_update(S, S->part[0], S->part[1], hs, seq);
+}
+__global__ void k_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq) {
+    scal_after_solvec(S, S->part[0], S->part[1], g.n_glob, hs, seq);
+}
+
+// ---------------------------------------------------------------- D(M)
+
+__global__ void __launch_bounds__(256) k_diffcoef(GridDesc g, NumParams np,
+                                                  const double *__restrict__ M,
+                                                  double *__restrict__ d, long long n2) {
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        const double2 m = ld2(M + 2 * i);
+        double2 o;
+        o.x = dfunc(m.x, np);
+        o.y = dfunc(m.y, np);
+        st2(d + 2 * i, o);
+    }
+}
+
+// ---------------------------------------------------------------- 5-point marching kernel
+
+enum { MODE_INIT = 0, MODE_CG = 1 };
+
+// Value of the vector the operator is applied to, at one cell.
+//   INIT: x0                                  (CG:46)
+//   CG:   r            first iteration        (CG:64)
+//         r + beta p   afterwards             (CG:71)
+template <int MODE>
+struct VecLoad {
+    const double *a, *b;
+    double beta;
+    bool first;
+    __device__ __forceinline__ double2 two(long long off) const {
+        if (MODE == MODE_INIT) return ld2(a + off);
+        const double2 r = ld2(a + off);
+        if (first) return r;
+        const double2 p = ld2(b + off);
+        double2 v;
+        v.x = r.x + beta * p.x;
+        v.y = r.y + beta * p.y;
+        return v;
+    }
+    __device__ __forceinline__ double one(long long off) const {
+        if (MODE == MODE_INIT) return a[off];
+        const double r = a[off];
+        if (first) return r;
+        return r + beta * b[off];
+    }
+};
+
+// One CTA marches TR rows down a strip of 2*BS columns; thread t owns columns
+// (2t, 2t+1) of the strip and keeps the rows above / at / below in registers.
+// West / east neighbours come from the adjacent lanes; the two edge lanes of
+// each warp fetch theirs from memory.
+template <int MODE, int BS>
+__global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
+    __shared__ double sm[64];
+    DevScal *S = a.S;
+    VecLoad<MODE> V;
+    if (MODE == MODE_CG) {
+        if (S->done) return;
+        V.a = a.r; V.b = a.p;
+        V.first = (S->nit == 0);
+        V.beta = V.first ? 0.0 : S->rho / S->rho_old;       // CG:68
+    } else {
+        V.a = a.x0; V.b = nullptr; V.first = true; V.beta = 0.0;
+    }
+    const GridDesc g = a.g;
+    const NumParams np = a.np;
+    const int lane = threadIdx.x & 31;
+    const int j0 = (blockIdx.x * BS + threadIdx.x) * 2;
+    const bool inrow = j0 < g.P;
+    const int i_begin = blockIdx.y * a.TR;
+    const int i_end = min(i_begin + a.TR, g.rows);
+    const double h = np.h;
+    const double2 zero2 = make_double2(0.0, 0.0);
+
+    double acc0 = 0.0, acc1 = 0.0;
+
+    // column roles (P:560, P:568)
+    const bool firstc0 = (j0 == 0);
+    const bool lastc0 = (j0 == g.col - 1), lastc1 = (j0 + 1 == g.col - 1);
+    const bool valid0 = j0 < g.col, valid1 = j0 + 1 < g.col;
+
+    long long off = (long long)i_begin * g.P + j0;
+    double2 vN = zero2, vC = zero2, dN = zero2, dC = zero2;
+    if (inrow) {
+        vN = V.two(off - g.P);
+        vC = V.two(off);
+        dN = ld2(a.d + off - g.P);
+        dC = ld2(a.d + off);
+    }
+    if (MODE == MODE_CG && a.write_ghost_top && i_begin == 0 && inrow)
+        st2(a.p + off - g.P, vN);
+
+    for (int i = i_begin; i < i_end; ++i, off += g.P) {
+        double2 vS = zero2, dS = zero2;
+        if (inrow) {
+            vS = V.two(off + g.P);
+            dS = ld2(a.d + off + g.P);
+        }
+        double vW0 = __shfl_up_sync(FULL, vC.y, 1);
+        double dW0 = __shfl_up_sync(FULL, dC.y, 1);
+        double vE1 = __shfl_down_sync(FULL, vC.x, 1);
+        double dE1 = __shfl_down_sync(FULL, dC.x, 1);
+        if (lane == 0 && inrow) { vW0 = V.one(off - 1); dW0 = a.d[off - 1]; }
+        if (lane == 31 && inrow) { vE1 = V.one(off + 2); dE1 = a.d[off + 2]; }
+
+        if (inrow) {
+            const int gi = g.row0 + i;
+            const bool first = (gi == 0);                               // P:552
+            const bool lastrow = (gi == g.grow - 1);
+            const bool quirkrow = (gi == g.grow - 2);                   // P:576 '>='
+            // face coefficients xCof*0.5*(diff(k)+diff(i))  (P:553)
+            const double aN0 = h * (dN.x + dC.x), aN1 = h * (dN.y + dC.y);
+            const double aS0 = h * (dS.x + dC.x), aS1 = h * (dS.y + dC.y);
+            const double aW0 = h * (dW0 + dC.x);
+            const double aM = h * (dC.y + dC.x);   // east of cell 0 == west of cell 1
+            const double aE1 = h * (dE1 + dC.y);
+
+            double2 ac2, q2;
+            double2 c2 = zero2, mp2 = zero2;
+            if (MODE == MODE_INIT) {
+                c2 = ld2(a.Cc + off);
+                mp2 = ld2(a.Mprev + off);
+            } else {
+                ac2 = ld2(a.ac + off);
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const bool firstc = c ? false : firstc0;
+                const bool lastc = c ? lastc1 : lastc0;
+                const bool lastq = lastrow || (quirkrow && lastc);
+                const double aN = c ? aN1 : aN0, aS = c ? aS1 : aS0;
+                const double aW = c ? aM : aW0, aE = c ? aE1 : aM;
+                const double xN = c ? vN.y : vN.x, xS = c ? vS.y : vS.x;
+                const double xC = c ? vC.y : vC.x;
+                const double xW = c ? vC.x : vW0, xE = c ? vE1 : vC.y;
+                // DIA entries after the four if/else blocks of P:552-582
+                const double A1 = first ? 0.0 : (lastq ? -(aN + aN) : -aN);
+                const double A5 = lastq ? 0.0 : (first ? -(aS + aS) : -aS);
+                const double A2 = firstc ? 0.0 : (lastc ? -(aW + aW) : -aW);
+                const double A4 = lastc ? 0.0 : (firstc ? -(aE + aE) : -aE);
+                double A3;
+                if (MODE == MODE_INIT) {
+                    // centre: blocks 1..4 in order, then - f + (1/tDel)  (P:554-585)
+                    const double t1 = first ? aS : aN;
+                    const double t2 = firstc ? aE : aW;
+                    const double t3 = lastc ? aW : aE;
+                    const double t4 = lastq ? aN : aS;
+                    const double f = ffunc(c ? mp2.y : mp2.x, c ? c2.y : c2.x, np);
+                    A3 = (((t1 + t2) + t3) + t4) - f + np.inv_dt;
+                    if (c) ac2.y = A3; else ac2.x = A3;
+                } else {
+                    A3 = c ? ac2.y : ac2.x;
+                }
+                // amuxd: diagonals 1..5 accumulated in order (P:1093-1100)
+                double y = A1 * xN;
+                y = y + A2 * xW;
+                y = y + A3 * xC;
+                y = y + A4 * xE;
+                y = y + A5 * xS;
+                const bool valid = c ? valid1 : valid0;
+                if (MODE == MODE_INIT) {
+                    const double rhs = (c ? mp2.y : mp2.x) / np.tDel;       // P:586
+                    const double rr = valid ? (rhs - y) : 0.0;              // CG:49
+                    if (c) q2.y = rr; else q2.x = rr;
+                    acc0 += rr * rr;
+                    acc1 += valid ? xC * xC : 0.0;
+                    if (!valid) { if (c) ac2.y = 0.0; else ac2.x = 0.0; }
+                } else {
+                    const double qq = valid ? y : 0.0;
+                    if (c) q2.y = qq; else q2.x = qq;
+                    acc0 += xC * qq;                                        // CG:76
+                    acc1 += valid ? xC * xC : 0.0;                          // CG:87
+                }
+            }
+            if (MODE == MODE_INIT) {
+                st2(a.ac + off, ac2);
+                st2(a.r + off, q2);
+                if (a.x != a.x0) st2(a.x + off, vC);
+            } else {
+                st2(a.p + off, vC);
+                st2(a.q + off, q2);
+            }
+        }
+        vN = vC; vC = vS; dN = dC; dC = dS;
+    }
+    if (MODE == MODE_CG && a.write_ghost_bot && i_end == g.rows && inrow)
+        st2(a.p + off, vC);
+
+    const int nb = gridDim.x * gridDim.y;
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm)) {
+        if (a.fuse_scalars) {
+            if (MODE == MODE_INIT) scal_after_init(S, acc0, acc1);
+            else scal_after_spmv(S, acc0, acc1, g.n_glob, np.tol2, a.trace, a.hs);
+        } else {
+            S->part[0] = acc0; S->part[1] = acc1;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- CG vector update
+
+// sol += alfa p ; r -= alfa q (CG:79-82) and the two sums the next iteration
+// opens with: dotProd(r,r) (CG:59) and sum(sol*sol) (CG:57).  Pad cells hold
+// zeros in all four vectors, so the arrays are streamed flat.
+__global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
+    __shared__ double sm[64];
+    DevScal *S = a.S;
+    if (S->finished) return;
+    const double alfa = S->alfa;
+    double rr = 0.0, xx = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < a.n2; i += 2 * stride) {
+        const long long k0 = 2 * i, k1 = 2 * (i + stride);
+        double2 x0 = ld2(a.x + k0), p0 = ld2(a.p + k0), r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
+        double2 x1 = ld2(a.x + k1), p1 = ld2(a.p + k1), r1 = ld2(a.r + k1), q1 = ld2(a.q + k1);
+        x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
+        r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
+        x1.x = x1.x + alfa * p1.x; x1.y = x1.y + alfa * p1.y;
+        r1.x = r1.x - alfa * q1.x; r1.y = r1.y - alfa * q1.y;
+        st2(a.x + k0, x0); st2(a.r + k0, r0);
+        st2(a.x + k1, x1); st2(a.r + k1, r1);
+        rr += r0.x * r0.x; rr += r0.y * r0.y; rr += r1.x * r1.x; rr += r1.y * r1.y;
+        xx += x0.x * x0.x; xx += x0.y * x0.y; xx += x1.x * x1.x; xx += x1.y * x1.y;
+    }
+    for (; i < a.n2; i += stride) {
+        const long long k0 = 2 * i;
+        double2 x0 = ld2(a.x + k0), p0 = ld2(a.p + k0), r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
+        x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
+        r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
+        st2(a.x + k0, x0); st2(a.r + k0, r0);
+        rr += r0.x * r0.x; rr += r0.y * r0.y;
+        xx += x0.x * x0.x; xx += x0.y * x0.y;
+    }
+    if (grid_sum2(rr, xx, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_UPDATE], sm)) {
+        if (a.fuse_scalars) scal_after_update(S, rr, xx, a.hs, a.seq);
+        else { S->part[0] = rr; S->part[1] = xx; }
+    }
+}
+
+// ---------------------------------------------------------------- C update + Picard residuals
+
+// P:504-506
+__device__ __forceinline__ double solve_c_cell(double Mp, double Mn, double Cp,
+                                               const NumParams &np) {
+    const double g = Cp * Mp / (np.kappa + Cp);
+    const double b = np.kappa - Cp + np.aux * (Mn + g);
+    const double c = -np.kappa * Cp + np.aux * np.kappa * Cp * Mp / (np.kappa + Cp);
+    return 0.5 * (-b + sqrt(b * b - 4.0 * c));
+}
+
+__global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
+    __shared__ double sm[64];
+    const GridDesc g = a.g;
+    const NumParams np = a.np;
+    double dC = 0.0, dM = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n2; i += stride) {
+        const long long k = 2 * i;
+        const int j = (int)(k % g.P);
+        const bool v0 = j < g.col, v1 = j + 1 < g.col;
+        const double2 mp = ld2(a.Mprev + k), mn = ld2(a.Mnew + k), cp = ld2(a.Cprev + k);
+        const double2 cc = ld2(a.Ccur + k), mc = ld2(a.Mcur + k);
+        double2 cn;
+        cn.x = v0 ? solve_c_cell(mp.x, mn.x, cp.x, np) : 0.0;
+        cn.y = v1 ? solve_c_cell(mp.y, mn.y, cp.y, np) : 0.0;
+        if (np.gSelect == 1) st2(a.Cnew + k, cn);        // P:501
+        else cn = ld2(a.Cnew + k);                        // Cnew left as it was
+        dC += v0 ? fabs(cc.x - cn.x) : 0.0;               // P:958
+        dC += v1 ? fabs(cc.y - cn.y) : 0.0;
+        dM += v0 ? fabs(mc.x - mn.x) : 0.0;
+        dM += v1 ? fabs(mc.y - mn.y) : 0.0;
+    }
+    if (grid_sum2(dC, dM, a.partials, gridDim.x, blockIdx.x, &a.S->ticket[TICKET_SOLVEC], sm)) {
+        if (a.fuse_scalars) scal_after_solvec(a.S, dC, dM, g.n_glob, a.hs, a.seq);
+        else { a.S->part[0] = dC; a.S->part[1] = dM; }
+    }
+}
+
+// ---------------------------------------------------------------- diagnostics
+
+// calcMass (P:783-787) for M and C, and calcPeakInterface (P:989-1001): the
+// last cell in row-major order holding the maximum of M (ties: '>=' keeps the
+// later cell, P:993; the running maximum starts at 0, P:988) and the last row
+// with some M > 0.1 (P:997).
+__global__ void __launch_bounds__(256) k_mass(const MassArgs a) {
+    __shared__ double sm[64];
+    __shared__ double s_v[8];
+    __shared__ long long s_i[8];
+    __shared__ int s_r[8];
+    __shared__ int s_last;
+    const GridDesc g = a.g;
+    double sM = 0.0, sC = 0.0;
+    double bv = -1.0; long long bi = -1; int ir = -1;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n2; i += stride) {
+        const long long k = 2 * i;
+        const int li = (int)(k / g.P);
+        const int j = (int)(k - (long long)li * g.P);
+        const double2 m = ld2(a.M + k), c = ld2(a.C + k);
+        const long long gidx = (long long)(g.row0 + li) * g.col + j;
+#pragma unroll
+        for (int cdx = 0; cdx < 2; ++cdx) {
+            if (j + cdx < g.col) {
+                const double mv = cdx ? m.y : m.x;
+                sM += mv;
+                sC += cdx ? c.y : c.x;
+                if (mv >= 0.0 && (mv > bv || (mv == bv && gidx + cdx > bi))) { bv = mv; bi = gidx + cdx; }
+                if (mv > 0.1) ir = max(ir, g.row0 + li);
+            }
+        }
+    }
+    // block reduce
+    for (int o = 16; o > 0; o >>= 1) {
+        const double ov = __shfl_xor_sync(FULL, bv, o);
+        const long long oi = __shfl_xor_sync(FULL, bi, o);
+        const int orr = __shfl_xor_sync(FULL, ir, o);
+        if (ov > bv || (ov == bv && oi > bi)) { bv = ov; bi = oi; }
+        ir = max(ir, orr);
+    }
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    if (lane == 0) { s_v[w] = bv; s_i[w] = bi; s_r[w] = ir; }
+    block_sum2(sM, sC, sm);   // contains __syncthreads
+    const int nb = gridDim.x;
+    double *pS = a.partials;
+    double *pV = a.partials + 2 * nb;
+    long long *pI = reinterpret_cast<long long *>(a.partials + 3 * nb);
+    long long *pR = reinterpret_cast<long long *>(a.partials + 4 * nb);
+    if (threadIdx.x == 0) {
+        for (int k = 1; k < (int)(blockDim.x >> 5); ++k) {
+            if (s_v[k] > bv || (s_v[k] == bv && s_i[k] > bi)) { bv = s_v[k]; bi = s_i[k]; }
+            ir = max(ir, s_r[k]);
+        }
+        pS[blockIdx.x] = sM; pS[nb + blockIdx.x] = sC;
+        pV[blockIdx.x] = bv; pI[blockIdx.x] = bi; pR[blockIdx.x] = ir;
+        __threadfence();
+        const unsigned int t = atomicAdd(&a.S->ticket[TICKET_MASS], 1u);
+        s_last = (t == (unsigned int)(nb - 1));
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x == 0) {
+        // serial, fixed order: nb is a few hundred at most
+        double tM = 0.0, tC = 0.0, v = -1.0; long long vi = -1; long long r = -1;
+        for (int k = 0; k < nb; ++k) {
+            tM += __ldcg(pS + k); tC += __ldcg(pS + nb + k);
+            const double ov = __ldcg(pV + k); const long long oi = __ldcg(pI + k);
+            if (ov > v || (ov == v && oi > vi)) { v = ov; vi = oi; }
+            const long long orr = __ldcg(pR + k);
+            if (orr > r) r = orr;
+        }
+        a.S->sumM = tM; a.S->sumC = tC;
+        a.S->peak_val = v; a.S->peak_idx = vi; a.S->intfac_row = (int)r;
+        a.S->ticket[TICKET_MASS] = 0u;
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- launchers
+
+void kernel_config_from_env() {
+    if (const char *e = getenv("PDEODE_BS")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) g_bs_stencil = v;
+    }
+    if (const char *e = getenv("PDEODE_STREAM_CTAS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 32) g_stream_ctas_per_sm = v;
+    }
+    int dev = 0, sms = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
+        g_num_sms = sms;
+}
+
+int stream_blocks() { return g_num_sms * g_stream_ctas_per_sm; }
+
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static int flat_blocks(long long n2) {
+    const long long want = (n2 + 255) / 256;
+    const long long cap = stream_blocks();
+    return (int)(want < cap ? (want > 0 ? want : 1) : cap);
+}
+
+int stencil_max_blocks(const GridDesc &g, int TR) {
+    return cdiv(g.P, 2 * 64) * cdiv(g.rows, TR);
+}
+
+cudaError_t launch_diffcoef(const GridDesc &g, const NumParams &np, const double *M, double *d,
+                            cudaStream_t st) {
+    const long long n2 = (long long)g.rows * g.P / 2;
+    k_diffcoef<<<flat_blocks(n2), 256, 0, st>>>(g, np, M, d, n2);
+    return cudaGetLastError();
+}
+
+template <int MODE>
+static cudaError_t launch_stencil(const StencilArgs &a, cudaStream_t st) {
+    const int bs = g_bs_stencil;
+    dim3 grid(cdiv(a.g.P, 2 * bs), cdiv(a.g.rows, a.TR));
+    if (bs == 64) k_stencil<MODE, 64><<<grid, 64, 0, st>>>(a);
+    else if (bs == 256) k_stencil<MODE, 256><<<grid, 256, 0, st>>>(a);
+    else k_stencil<MODE, 128><<<grid, 128, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_stencil_init(const StencilArgs &a, cudaStream_t st) {
+    return launch_stencil<MODE_INIT>(a, st);
+}
+cudaError_t launch_stencil_cg(const StencilArgs &a, cudaStream_t st) {
+    return launch_stencil<MODE_CG>(a, st);
+}
+
+cudaError_t launch_update(const UpdateArgs &a, cudaStream_t st) {
+    k_update<<<flat_blocks((a.n2 + 1) / 2), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st) {
+    k_solvec<<<flat_blocks(a.n2), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_mass(const MassArgs &a, cudaStream_t st) {
+    int nb = flat_blocks(a.n2);
+    if (nb > 296) nb = 296;
+    k_mass<<<nb, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_scal_after_init(DevScal *S, cudaStream_t st) {
+    k_scal_after_init<<<1, 1, 0, st>>>(S);
+    return cudaGetLastError();
+}
+cudaError_t launch_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace,
+                                   HostStatus *hs, long long, cudaStream_t st) {
+    k_scal_after_spmv<<<1, 1, 0, st>>>(S, g, tol2, trace, hs);
+    return cudaGetLastError();
+}
+cudaError_t launch_scal_after_update(DevScal *S, HostStatus *hs, long long seq, cudaStream_t st) {
+    k_scal_after_update<<<1, 1, 0, st>>>(S, hs, seq);
+    return cudaGetLastError();
+}
+cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq,
+                                     cudaStream_t st) {
+    k_scal_after_solvec<<<1, 1, 0, st>>>(S, g, hs, seq);
+    return cudaGetLastError();
+}
+
+}  // namespace pdeode

@@ -1,0 +1,297 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU
+oracle and the committed golden fixtures.
+
+Bars (BASELINE.json north_star): M and C within a relative L2 error of 1e-9,
+CG iteration counts within +-2 per solve, Picard counts exact.  Element-wise
+kernels are held to bit-exactness (no FMA, same operation order as the
+reference); only reductions may differ, at rounding level.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+import oracle_lib as ol
+from test_golden_oracle import CASES, load_case
+
+pytestmark = pytest.mark.gpu
+
+TOL_FIELD = 1e-9      # relative L2, north_star
+TOL_CG = 2            # iterations per solve, north_star
+
+
+@pytest.fixture(scope="module")
+def pb():
+    import __graft_entry__ as ge
+    ge.build_cuda()
+    ol.build_oracle()
+    import pdeode_b200
+    return pdeode_b200
+
+
+def rel_l2(a, b):
+    nb = np.linalg.norm(b)
+    return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
+
+
+def run_pair(pb, row, col, over, M0, C0, steps, check_every=True):
+    s = pb.Solver(row, col, pb.default_params(row, **over))
+    o = ol.Oracle(row, col, ol.default_params(row, **over))
+    s.set_state(M0, C0)
+    o.set_state(M0, C0)
+    worst = 0.0
+    for k in range(steps):
+        g = s.step_trace()
+        r = o.step()
+        assert (g["rc"] & pb.ERR_MASK) == 0
+        assert g["countIters"] == r["countIters"], (k, g, r)          # Picard: exact
+        assert len(g["nits"]) == len(r["nits"])
+        for a, b in zip(g["nits"], r["nits"]):
+            assert abs(a - b) <= TOL_CG, (k, g["nits"], r["nits"])
+        assert g["nitSum"] == sum(g["nits"]) and g["nitMax"] == max(g["nits"])
+        if check_every or k == steps - 1:
+            Mg, Cg = s.get_state()
+            Mo, Co = o.get_state()
+            eM, eC = rel_l2(Mg, Mo), rel_l2(Cg, Co)
+            worst = max(worst, eM, eC)
+            assert eM <= TOL_FIELD and eC <= TOL_FIELD, (k, eM, eC)
+    s.close(); o.close()
+    return worst
+
+
+# ------------------------------------------------------------ element-wise: bit-exact
+
+@pytest.mark.parametrize("row,col", [(5, 5), (9, 4), (33, 33), (37, 53), (64, 48), (20, 257)])
+@pytest.mark.parametrize("fsel,dsel", [(1, 3), (3, 2), (6, 1), (5, 3), (2, 3), (4, 3)])
+def test_assembly_spmv_and_c_update_bit_exact(pb, row, col, fsel, dsel):
+    """One Picard iterate with a one-iteration CG (maxit = 0 -> CG:88 stops after
+    iteration 1): D(M), the centre diagonal, q = A p with p = rhs, and the C
+    update must equal the oracle's bit for bit, boundary rows, the P:576 quirk
+    cell and pad columns included."""
+    rng = np.random.RandomState(row * 1000 + col)
+    n = row * col
+    M0 = rng.uniform(0.05, 0.85, n); C0 = rng.uniform(0.2, 1.0, n)
+    over = dict(fSelect=fsel, dSelect=dsel, eSoln=1.5)     # exactly one Picard iterate
+    p = pb.default_params(row, **over)
+    s = pb.Solver(row, col, p)
+    s.set_state(M0, C0)
+    s.set_maxit(0)
+    g = s.step_trace()
+    assert g["countIters"] == 1 and g["nits"] == [1]
+    assert g["rc"] & pb.WARN_CG_CAP
+
+    lib = ol.load()
+    po = ol.default_params(row, **over)
+    A = np.zeros(5 * n); rhs = np.zeros(n); ioff = np.zeros(5, np.int32)
+    lib.oracle_gen_matrix(M0, C0, A, ioff, rhs, row, col, C.byref(po))
+    d_want = np.array([lib.oracle_dfunc(m, po.delta, po.alpha, po.beta, po.dSelect) for m in M0])
+    assert np.array_equal(s.array(pb.ARR_D), d_want)
+    assert np.array_equal(s.array(pb.ARR_AC), A[2 * n:3 * n])
+    # x0 = 0  ->  r0 = rhs, p1 = r0, q1 = A p1
+    assert np.array_equal(s.array(pb.ARR_P), rhs)
+    q_want = np.empty(n)
+    lib.oracle_amuxd(n, rhs, q_want, A, 5, ioff)
+    assert np.array_equal(s.array(pb.ARR_Q), q_want)
+    # C update from the GPU's own Mnew: bit-exact
+    Mnew = s.array(pb.ARR_MNEW)
+    Cn = np.empty(n)
+    lib.oracle_solve_c(M0, Mnew, C0, Cn, n, po.kappa, po.gama, po.tDel, 1)
+    Mg, Cg = s.get_state()
+    assert np.array_equal(Cg, Cn)
+    assert np.array_equal(Mg, Mnew)
+    # x1 = alfa p, r1 = r0 - alfa q: alfa from the device's own sums
+    _, tr = None, None
+    s.close()
+
+
+def test_first_cg_iteration_scalars(pb):
+    """rho, p.q, alfa, err2, normx of each CG iteration against the oracle's
+    serial sums (reductions differ in order only)."""
+    row = col = 65
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    s = pb.Solver(row, col, pb.default_params(row, eSoln=1.5))
+    s.cg_trace_enable(512)
+    s.set_state(M0, C0)
+    g = s.step_trace()
+    n_g, tg = s.cg_trace(512)
+    o = ol.Oracle(row, col, ol.default_params(row))
+    o.set_state(M0, C0)
+    n_o, to = o.first_solve_trace(512)
+    assert n_g == g["nits"][0]
+    assert abs(n_g - n_o) <= TOL_CG
+    for k in range(min(n_g, n_o)):
+        for key in ("rho", "dot", "alfa", "err2", "normx"):
+            a, b = tg[k][key], to[k][key]
+            assert a == pytest.approx(b, rel=1e-9, abs=1e-300), (k, key, a, b)
+    # early iterations agree to rounding
+    for key in ("rho", "dot", "alfa"):
+        assert tg[0][key] == pytest.approx(to[0][key], rel=1e-13)
+    assert tg[0]["normx"] == 0.0          # x0 = 0 (D8): iteration 1 can never stop
+    s.close()
+
+
+# ------------------------------------------------------------ whole steps vs oracle
+
+@pytest.mark.parametrize("row,col,over,ic,steps", [
+    (33, 33, {}, ("ic1", 0.9, 0.3), 4),
+    (257, 4, {}, ("ic1", 0.9, 0.3), 6),                       # true2D = 1 layout (P:91-93)
+    (65, 65, {}, ("blobs", 0.25, 0.2, 8, 3), 4),
+    (129, 129, {}, ("ic1", 0.9, 0.3), 3),
+    (37, 53, dict(fSelect=3), ("ic1", 0.7, 0.4), 3),          # odd, non-square, pad columns
+    (50, 300, dict(fSelect=6, dSelect=2, alpha=2), ("blobs", 0.3, 0.2, 5, 1), 3),
+    (64, 64, dict(dSelect=1, fSelect=5, tDel=1e-2), ("blobs", 0.3, 0.3, 4, 2), 3),
+    (257, 257, {}, ("blobs", 0.02, 0.0390625, 60, 7), 4),     # shipped parameter.txt values
+])
+def test_steps_match_oracle(pb, row, col, over, ic, steps):
+    if ic[0] == "ic1":
+        M0, C0 = ol.ic1(row, col, ic[1], ic[2])
+    else:
+        M0, C0 = ol.ic_blobs(row, col, ic[1], ic[2], ic[3], ic[4])
+    run_pair(pb, row, col, over, M0, C0, steps)
+
+
+def test_1024_grid_matches_oracle(pb):
+    """BASELINE config 2: 1024^2, shipped parameters; plus a diffusive start."""
+    row = col = 1024
+    M0, C0 = ol.ic_blobs(row, col, 0.02, 0.0390625, 60, 11)
+    run_pair(pb, row, col, {}, M0, C0, 3, check_every=False)
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    run_pair(pb, row, col, {}, M0, C0, 1)
+
+
+@pytest.mark.parametrize("name", CASES)
+def test_golden_fixtures(pb, name):
+    z, row, col, over = load_case(name)
+    s = pb.Solver(row, col, pb.default_params(row, **over))
+    s.set_state(z["M0"], z["C0"])
+    for k in range(int(z["steps"])):
+        g = s.step_trace()
+        assert g["countIters"] == z["countIters"][k]
+        for a, b in zip(g["nits"], z["nits"][k]):
+            assert abs(a - int(b)) <= TOL_CG, (name, k, g["nits"], z["nits"][k])
+        M, Cc = s.get_state()
+        assert rel_l2(M, z[f"M{k + 1}"]) <= TOL_FIELD
+        assert rel_l2(Cc, z[f"C{k + 1}"]) <= TOL_FIELD
+    s.close()
+
+
+# ------------------------------------------------------------ diagnostics
+
+def test_mass_and_peak_match_oracle(pb):
+    row, col = 257, 4
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    s = pb.Solver(row, col, pb.default_params(row))
+    o = ol.Oracle(row, col, ol.default_params(row))
+    s.set_state(M0, C0); o.set_state(M0, C0)
+    lib = ol.load()
+    for k in range(5):
+        Mo, Co = o.get_state()
+        mM, mC = s.mass()
+        assert mM == pytest.approx(lib.oracle_calc_mass(Mo, Mo.size), rel=1e-12)
+        assert mC == pytest.approx(lib.oracle_calc_mass(Co, Co.size), rel=1e-12)
+        pk, he, itf = C.c_double(-1), C.c_double(-1), C.c_double(-1)
+        lib.oracle_calc_peak_interface(Mo, row, col, C.byref(pk), C.byref(he), C.byref(itf))
+        gp, gh, gi = s.peak(-1.0, -1.0, -1.0)
+        assert gp == pk.value and gi == itf.value
+        assert gh == pytest.approx(he.value, rel=1e-12)
+        s.step(); o.step()
+    s.close()
+
+
+def test_peak_tie_and_unassigned_interface(pb):
+    row, col = 6, 4
+    M = np.zeros(row * col)
+    M[1 * col + 2] = 0.05; M[3 * col + 0] = 0.05
+    s = pb.Solver(row, col, pb.default_params(row))
+    s.set_state(M, np.ones(row * col))
+    pk, he, itf = s.peak(-3.0, -3.0, -7.0)
+    assert he == 0.05 and pk == 3 / 5          # last maximal cell wins (P:993)
+    assert itf == -7.0                         # never assigned (D8)
+    s.set_state(np.zeros(row * col), np.ones(row * col))
+    pk, he, itf = s.peak(-3.0, -3.0, -7.0)
+    assert pk == 1.0 and he == 0.0
+    s.close()
+
+
+# ------------------------------------------------------------ properties at full size
+
+def test_homogeneous_4096(pb):
+    """K2 at BASELINE's 4096^2: a uniform state stays uniform and follows the
+    scalar recurrence; CG takes 2 then 1 iterations; Picard 2."""
+    row = col = 4096
+    p = pb.default_params(row)
+    s = pb.Solver(row, col, p)
+    M0 = np.full(row * col, 0.02); C0 = np.ones(row * col)
+    s.set_state(M0, C0)
+    m, c = 0.02, 1.0
+    for step in range(2):
+        g = s.step_trace()
+        assert g["countIters"] == 2 and g["nits"] == [2, 1]
+        ck = c
+        for _ in range(2):
+            f = ck / (p.kappa + ck) - p.nu
+            mk = m / (1 - p.tDel * f)
+            aux = 0.5 * p.tDel * p.gama
+            b = p.kappa - c + aux * (mk + c * m / (p.kappa + c))
+            cc = -p.kappa * c + aux * p.kappa * c * m / (p.kappa + c)
+            ck = 0.5 * (-b + np.sqrt(b * b - 4 * cc))
+        m, c = mk, ck
+    M, Cc = s.get_state()
+    assert M.max() - M.min() < 1e-15 and Cc.max() - Cc.min() < 1e-15
+    assert M[0] == pytest.approx(m, rel=1e-12) and Cc[0] == pytest.approx(c, rel=1e-12)
+    mM, mC = s.mass()
+    assert mM == pytest.approx(m, rel=1e-12) and mC == pytest.approx(c, rel=1e-12)
+    s.close()
+
+
+def test_linear_system_residual_4096(pb):
+    """Size-independent property: after a solve, A.Mnew = Mprev/tDel to the
+    solver's tolerance.  Checked through a second context: one INIT pass with
+    x0 = the solution leaves r = b - A x, whose norm must be tiny."""
+    row = col = 4096
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    s = pb.Solver(row, col, pb.default_params(row, eSoln=1.5))
+    s.set_state(M0, C0)
+    g = s.step_trace()
+    assert g["countIters"] == 1 and g["nits"][0] > 100
+    r = s.array(pb.ARR_R)
+    rhs = M0 / 1e-3
+    assert np.linalg.norm(r) <= 1e-5 * np.linalg.norm(rhs)
+    # run-to-run determinism of the whole step (fixed-order reductions)
+    M1, C1 = s.get_state()
+    s.set_state(M0, C0)
+    g2 = s.step_trace()
+    M2, C2 = s.get_state()
+    assert g2["nits"] == g["nits"]
+    assert np.array_equal(M1, M2) and np.array_equal(C1, C2)
+    s.close()
+
+
+def test_cg_cap_is_reported_not_fatal(pb):
+    row = col = 65
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    s = pb.Solver(row, col, pb.default_params(row))
+    o = ol.Oracle(row, col, ol.default_params(row))
+    s.set_state(M0, C0); o.set_state(M0, C0)
+    s.set_maxit(5); o.set_maxit(5)
+    g = s.step_trace(); r = o.step()
+    assert g["rc"] & pb.WARN_CG_CAP
+    assert g["countIters"] == r["countIters"] and g["nits"] == r["nits"]
+    Mg, Cg = s.get_state(); Mo, Co = o.get_state()
+    assert rel_l2(Mg, Mo) <= TOL_FIELD and rel_l2(Cg, Co) <= TOL_FIELD
+    s.close()
+
+
+def test_set_state_resets_warm_start(pb):
+    row = col = 65
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    s = pb.Solver(row, col, pb.default_params(row))
+    s.set_state(M0, C0)
+    a = s.step_trace()
+    Ma, Ca = s.get_state()
+    s.set_state(M0, C0)
+    b = s.step_trace()
+    Mb, Cb = s.get_state()
+    assert a["nits"] == b["nits"]
+    assert np.array_equal(Ma, Mb) and np.array_equal(Ca, Cb)
+    s.close()
