@@ -184,8 +184,8 @@ def workload_config(args, nranks):
                     "(D(M), Picard loop, CG solves, C update)",
         "grid": [args.grid, args.grid],
         "parallelism": f"row-slabs x{nranks}" if nranks > 1 else "single GPU",
-        "l2": "inputs larger than L2: 11 fp64 fields of the grid stay resident "
-              f"({11 * 8 * args.grid * args.grid / 1e6:.0f} MB total vs 126 MB L2); no flush",
+        "l2": "inputs larger than L2: 12 fp64 fields of the grid stay resident "
+              f"({12 * 8 * args.grid * args.grid / 1e6:.0f} MB total vs 126 MB L2); no flush",
     }
 
 
@@ -201,6 +201,7 @@ def main():
     ap.add_argument("--ref-cg-iters", type=int, default=24)
     ap.add_argument("--cpu-cg-iters", type=int, default=120)
     ap.add_argument("--kernel-reps", type=int, default=50)
+    ap.add_argument("--cg-cap", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -235,8 +236,9 @@ def main():
     n = row * col
     params = pb.default_params(row)
     s = pb.Solver(row, col, params, device=local, rank=rank, nranks=world, nccl_id=nccl_id)
-    stream = torch.cuda.current_stream()
+    stream = torch.cuda.Stream()           # the library launches here; events are recorded here
     s.set_stream(stream.cuda_stream)
+    s.set_maxit(args.cg_cap)               # safety net only; a hit invalidates the run (checked below)
     M0, C0 = ic1(row, col, args.height, args.depth)
     lo, hi = s.row0 * col, (s.row0 + s.nrows) * col
     Mh = torch.from_numpy(M0[lo:hi].copy()).pin_memory()
@@ -268,7 +270,10 @@ def main():
     s.set_state_ptr(Mh.data_ptr(), Ch.data_ptr())
 
     def resident_step():
-        return s.step()["nitSum"]
+        r = s.step()
+        if r["rc"] != 0:
+            raise SystemExit(f"bench.py: pdeode_step returned {r['rc']} (CG cap or Picard cap hit)")
+        return r["nitSum"]
 
     for _ in range(args.warmup):
         resident_step()

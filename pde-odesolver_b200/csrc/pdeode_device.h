@@ -79,8 +79,13 @@ struct StencilArgs {
     double *trace;         // may be null; 5 doubles per CG iteration
     // INIT: x0 -> (ac, r, x);   CG: (r, p) -> (p, q)
     const double *x0, *d, *Cc, *Mprev;
-    double *ac, *r, *x, *p, *q;
+    const double *p_in;    // direction read by CG mode (never the array written: neighbours
+                           // recompute r + beta p from it, so p cannot be updated in place)
+    double *ac, *r, *x, *p, *q;  // p = direction written
     int TR;                // rows marched per CTA
+    int BS;                // consumer threads per CTA (64 | 128 | 256); strip = 2*BS columns
+    int DEPTH;             // ring depth in rows of the bulk-async variant
+    int variant;           // CG SpMV: 0 register-staged, 1 bulk-async staged (default)
     int fuse_scalars;      // 1: last block turns sums into alfa/stop (single rank)
     int write_ghost_top, write_ghost_bot; // maintain p ghost rows (multi rank)
     long long seq;
@@ -135,8 +140,14 @@ cudaError_t launch_scal_after_update(DevScal *S, HostStatus *hs, long long seq,
                                      cudaStream_t st);
 cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq,
                                      cudaStream_t st);
+// Launch shape of the 5-point kernels for one context.
+struct LaunchCfg {
+    int BS, TR, DEPTH, variant;
+};
+// Heuristic defaults for a grid, then PDEODE_BS / PDEODE_TR / PDEODE_DEPTH /
+// PDEODE_VARIANT (reg|bulk) overrides from the environment.
+LaunchCfg launch_config(const GridDesc &g);
 int stencil_max_blocks(const GridDesc &g, int TR);
 int stream_blocks();
-void kernel_config_from_env();
 
 }  // namespace pdeode

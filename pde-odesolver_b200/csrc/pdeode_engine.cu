@@ -41,7 +41,10 @@ struct pdeode_ctx {
     long long maxit = 0, maxit_default = 0;
 
     // field buffers: three M, three C (prev / current / new rotate), work arrays
-    double *base[11] = {nullptr};
+    static constexpr int NARR = 12;
+    double *base[NARR] = {nullptr};
+    double *pbuf[2] = {nullptr, nullptr};  // CG direction, ping-pong (see StencilArgs::p_in)
+    int ip = 0;                            // pbuf[ip] holds the current direction
     double *Mb[3] = {nullptr}, *Cb[3] = {nullptr};
     int iM = 0, iMprev = 0, iC = 0, iCprev = 0;
     int iMnew = 1;                // buffer holding the last CG solution
@@ -59,7 +62,7 @@ struct pdeode_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     ncclComm_t comm = nullptr;
 
-    int TR = 16;
+    LaunchCfg cfg{256, 64, 4, 1};
     int pred[MAX_PICARD_TRACE];
     long long seq = 0;
     long long launches = 0;
@@ -149,8 +152,9 @@ StencilArgs stencil_args(pdeode_ctx *c) {
     StencilArgs a{};
     a.g = c->g; a.np = c->np; a.S = c->S; a.partials = c->partials;
     a.hs = nullptr; a.trace = c->trace_cap > 0 ? c->trace : nullptr;
-    a.d = c->d; a.ac = c->ac; a.r = c->r; a.p = c->p; a.q = c->q;
-    a.TR = c->TR;
+    a.d = c->d; a.ac = c->ac; a.r = c->r; a.q = c->q;
+    a.p_in = c->pbuf[c->ip]; a.p = c->pbuf[c->ip ^ 1];
+    a.TR = c->cfg.TR; a.BS = c->cfg.BS; a.DEPTH = c->cfg.DEPTH; a.variant = c->cfg.variant;
     a.fuse_scalars = multi(c) ? 0 : 1;
     a.write_ghost_top = multi(c) && c->rank > 0;
     a.write_ghost_bot = multi(c) && c->rank < c->nranks - 1;
@@ -163,6 +167,8 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     StencilArgs a = stencil_args(c);
     CK(launch_stencil_cg(a, c->stream));
     c->launches++;
+    c->ip ^= 1;                      // the direction just written is the current one
+    c->p = c->pbuf[c->ip];
     if (multi(c)) {
         int rc = allreduce_part(c, 2);
         if (rc) return rc;
@@ -211,6 +217,7 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
 
     // CG iterations in chunks; the device flags convergence, later launches
     // of a finished solve return at once.
+    const int ip0 = c->ip;
     const int pred = std::max(1, c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)]);
     long long launched = 0;
     int slot = 0;
@@ -250,6 +257,10 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         chunk = (int)std::min<long long>(std::max<long long>(2, launched / 2), 1024);
     }
     const DevScal &fin = c->snap[slot].s;
+    // launches after convergence were no-ops: the direction of the last real
+    // iteration sits in the buffer given by the parity of nit
+    c->ip = ip0 ^ (int)(fin.nit & 1);
+    c->p = c->pbuf[c->ip];
     *nit_out = fin.nit;
     *stop_out = fin.stop;
     c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)] = (int)std::min<long long>(fin.nit, 1 << 20);
@@ -340,8 +351,6 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     *out = c;   // returned even on failure so that pdeode_last_error works; destroy it
     c->device = device; c->rank = rank; c->nranks = nranks; c->params = *p;
     CK(cudaSetDevice(device));
-    kernel_config_from_env();
-    if (const char *t = getenv("PDEODE_TR")) { int v = atoi(t); if (v >= 1 && v <= 4096) c->TR = v; }
 
     const int r0 = (int)((long long)rank * row / nranks);
     const int r1 = (int)((long long)(rank + 1) * row / nranks);
@@ -355,7 +364,7 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     for (int k = 0; k < MAX_PICARD_TRACE; ++k) c->pred[k] = (k == 0) ? 8 : 1;
 
     c->arr_doubles = (size_t)(c->g.rows + 2) * c->g.P + 2 * GUARD;
-    for (int k = 0; k < 11; ++k) {
+    for (int k = 0; k < pdeode_ctx::NARR; ++k) {
         cudaError_t me = cudaMalloc(&c->base[k], c->arr_doubles * sizeof(double));
         if (me != cudaSuccess) {
             fail_cuda(c, me, "cudaMalloc(field)");
@@ -365,11 +374,12 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     }
     auto origin = [&](int k) { return c->base[k] + GUARD + c->g.P; };
     for (int k = 0; k < 3; ++k) { c->Mb[k] = origin(k); c->Cb[k] = origin(3 + k); }
-    c->d = origin(6); c->ac = origin(7); c->r = origin(8); c->p = origin(9); c->q = origin(10);
+    c->d = origin(6); c->ac = origin(7); c->r = origin(8); c->q = origin(10);
+    c->pbuf[0] = origin(9); c->pbuf[1] = origin(11); c->ip = 0; c->p = c->pbuf[0];
 
-    c->max_blocks = std::max(stencil_max_blocks(c->g, 1), std::max(stream_blocks(), 512));
-    // the marching kernel never launches more CTAs than stencil_max_blocks(g, TR)
-    c->max_blocks = std::max(stencil_max_blocks(c->g, c->TR), std::max(stream_blocks(), 512));
+    c->cfg = launch_config(c->g);
+    // the marching kernels never launch more CTAs than stencil_max_blocks(g, TR)
+    c->max_blocks = std::max(stencil_max_blocks(c->g, c->cfg.TR), std::max(stream_blocks(), 512));
     CK(cudaMalloc(&c->partials, sizeof(double) * 8 * (size_t)c->max_blocks));
     CK(cudaMalloc(&c->S, sizeof(DevScal)));
     CK(cudaMemset(c->S, 0, sizeof(DevScal)));
@@ -436,7 +446,7 @@ int pdeode_destroy(pdeode_ctx *c) {
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->comm) nccl().CommDestroy(c->comm);
-    for (int k = 0; k < 11; ++k) if (c->base[k]) cudaFree(c->base[k]);
+    for (int k = 0; k < pdeode_ctx::NARR; ++k) if (c->base[k]) cudaFree(c->base[k]);
     if (c->partials) cudaFree(c->partials);
     if (c->S) cudaFree(c->S);
     if (c->trace) cudaFree(c->trace);

@@ -27,7 +27,6 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-int g_bs_stencil = 128;   // threads per CTA of the marching kernel
 int g_stream_ctas_per_sm = 8;
 int g_num_sms = 148;
 
@@ -254,7 +253,7 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
     VecLoad<MODE> V;
     if (MODE == MODE_CG) {
         if (S->done) return;
-        V.a = a.r; V.b = a.p;
+        V.a = a.r; V.b = a.p_in;
         V.first = (S->nit == 0);
         V.beta = V.first ? 0.0 : S->rho / S->rho_old;       // CG:68
     } else {
@@ -393,6 +392,218 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
         } else {
             S->part[0] = acc0; S->part[1] = acc1;
         }
+    }
+}
+
+// ---------------------------------------------------------------- CG SpMV, bulk-async staged
+
+// mbarrier / bulk-copy (TMA engine, 1-D form) primitives
+__device__ __forceinline__ unsigned smem_u32(const void *p) {
+    return (unsigned)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, unsigned count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+                 "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes,
+                                         unsigned long long *bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+            "r"(smem_u32(dst)),
+        "l"(src), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+
+// Same arithmetic as k_stencil<MODE_CG>, different data movement: one producer
+// lane streams the row segments of r, p, d and ac of a 2*BS-column strip into a
+// DEPTH-deep shared-memory ring with cp.async.bulk (the TMA engine), each row
+// arriving on its own mbarrier; BS consumer threads pick a landed row out of
+// shared memory, keep three rows in registers and march down.  Loads are in
+// flight DEPTH rows ahead of the arithmetic without costing registers, which
+// is what the register-staged version lacked (long-scoreboard bound at 35 %
+// occupancy).  Row segments carry a 2-double halo on both sides so the west /
+// east neighbours of the strip's edge columns come from the same copy.
+template <int BS, int DEPTH>
+__global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
+    constexpr int TC = 2 * BS;          // columns per strip
+    constexpr int SEG = TC + 4;         // doubles per staged row segment (halo 2 + 2)
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    double *s_r = reinterpret_cast<double *>(smem_raw);            // [DEPTH][SEG]
+    double *s_p = s_r + DEPTH * SEG;                               // [DEPTH][SEG]
+    double *s_d = s_p + DEPTH * SEG;                               // [DEPTH][SEG]
+    double *s_ac = s_d + DEPTH * SEG;                              // [DEPTH][TC]
+    unsigned long long *full = reinterpret_cast<unsigned long long *>(s_ac + DEPTH * TC);
+    unsigned long long *empty = full + DEPTH;
+    __shared__ double sm[64];
+
+    DevScal *S = a.S;
+    if (S->done) return;
+    const bool firstit = (S->nit == 0);
+    const double beta = firstit ? 0.0 : S->rho / S->rho_old;       // CG:68
+    const GridDesc g = a.g;
+    const int tid = threadIdx.x;
+    const int jt = blockIdx.x * TC;                 // first column of the strip
+    const int i_begin = blockIdx.y * a.TR;
+    const int i_end = min(i_begin + a.TR, g.rows);
+    const int nstage = (i_end - i_begin) + 2;       // rows i_begin-1 .. i_end
+    // segment [jt-2, jt-2+seglen): never past 2 doubles beyond the row (guard)
+    const int seglen = min(SEG, g.P + 4 - jt);
+    const unsigned segbytes = (unsigned)seglen * 8u;
+    const int aclen = min(TC, g.P - jt);
+    const unsigned acbytes = (unsigned)aclen * 8u;
+
+    if (tid == 0) {
+        for (int s = 0; s < DEPTH; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    double acc0 = 0.0, acc1 = 0.0;
+
+    if (tid >= BS) {
+        // ---------------- producer warp: one lane issues the copies
+        if (tid == BS) {
+            for (int k = 0; k < nstage; ++k) {
+                const int s = k % DEPTH;
+                if (k >= DEPTH) mbar_wait(&empty[s], ((k / DEPTH) - 1) & 1);
+                const int i = i_begin - 1 + k;
+                const long long off = (long long)i * g.P + (jt - 2);
+                const bool has_ac = (k >= 1 && k <= nstage - 2);
+                const unsigned tx = segbytes * (firstit ? 2u : 3u) + (has_ac ? acbytes : 0u);
+                mbar_expect_tx(&full[s], tx);
+                bulk_g2s(s_r + s * SEG, a.r + off, segbytes, &full[s]);
+                if (!firstit) bulk_g2s(s_p + s * SEG, a.p_in + off, segbytes, &full[s]);
+                bulk_g2s(s_d + s * SEG, a.d + off, segbytes, &full[s]);
+                if (has_ac) bulk_g2s(s_ac + s * TC, a.ac + off + 2, acbytes, &full[s]);
+            }
+        }
+    } else {
+        // ---------------- consumers
+        const int lane = tid & 31;
+        const int j0 = jt + 2 * tid;
+        const bool inrow = j0 < g.P;
+        const double h = a.np.h;
+        const bool firstc0 = (j0 == 0);
+        const bool lastc0 = (j0 == g.col - 1), lastc1 = (j0 + 1 == g.col - 1);
+        const bool valid0 = j0 < g.col, valid1 = j0 + 1 < g.col;
+        const int c0 = 2 * tid + 2;                  // my pair inside a staged segment
+        const int ce = (lane == 0) ? c0 - 1 : c0 + 2;  // edge lanes: west / east halo cell
+
+        double2 vN, vC, vS, dN, dC, dS, acC, acS;
+        double veC = 0.0, deC = 0.0, veS = 0.0, deS = 0.0;   // edge-lane neighbours
+        vN = vC = vS = dN = dC = dS = acC = acS = make_double2(0.0, 0.0);
+
+        // fetch one staged row into (v, d, ac, ve, de)
+        auto take = [&](int k, double2 &v, double2 &d, double2 &ac, double &ve, double &de) {
+            const int s = k % DEPTH;
+            mbar_wait(&full[s], (k / DEPTH) & 1);
+            const double *sr = s_r + s * SEG, *sp = s_p + s * SEG, *sd = s_d + s * SEG;
+            if (inrow) {
+                const double2 r2 = *reinterpret_cast<const double2 *>(sr + c0);
+                d = *reinterpret_cast<const double2 *>(sd + c0);
+                ac = *reinterpret_cast<const double2 *>(s_ac + s * TC + 2 * tid);
+                if (firstit) {
+                    v = r2;                                            // CG:64
+                } else {
+                    const double2 p2 = *reinterpret_cast<const double2 *>(sp + c0);
+                    v.x = r2.x + beta * p2.x;                          // CG:71
+                    v.y = r2.y + beta * p2.y;
+                }
+                if (lane == 0 || lane == 31) {
+                    ve = firstit ? sr[ce] : sr[ce] + beta * sp[ce];
+                    de = sd[ce];
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[s]);
+        };
+
+        double2 dummy;
+        double dum1, dum2;
+        take(0, vN, dN, dummy, dum1, dum2);
+        take(1, vC, dC, acC, veC, deC);
+        long long off = (long long)i_begin * g.P + j0;
+        if (a.write_ghost_top && i_begin == 0 && inrow) st2(a.p + off - g.P, vN);
+
+        for (int i = i_begin; i < i_end; ++i, off += g.P) {
+            take(i - i_begin + 2, vS, dS, acS, veS, deS);
+            double vW0 = __shfl_up_sync(FULL, vC.y, 1);
+            double dW0 = __shfl_up_sync(FULL, dC.y, 1);
+            double vE1 = __shfl_down_sync(FULL, vC.x, 1);
+            double dE1 = __shfl_down_sync(FULL, dC.x, 1);
+            if (lane == 0) { vW0 = veC; dW0 = deC; }
+            if (lane == 31) { vE1 = veC; dE1 = deC; }
+            if (inrow) {
+                const int gi = g.row0 + i;
+                const bool first = (gi == 0);
+                const bool lastrow = (gi == g.grow - 1);
+                const bool quirkrow = (gi == g.grow - 2);
+                const double aN0 = h * (dN.x + dC.x), aN1 = h * (dN.y + dC.y);
+                const double aS0 = h * (dS.x + dC.x), aS1 = h * (dS.y + dC.y);
+                const double aW0 = h * (dW0 + dC.x);
+                const double aM = h * (dC.y + dC.x);
+                const double aE1 = h * (dE1 + dC.y);
+                double2 q2;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const bool firstc = c ? false : firstc0;
+                    const bool lastc = c ? lastc1 : lastc0;
+                    const bool lastq = lastrow || (quirkrow && lastc);
+                    const double aN = c ? aN1 : aN0, aS = c ? aS1 : aS0;
+                    const double aW = c ? aM : aW0, aE = c ? aE1 : aM;
+                    const double xN = c ? vN.y : vN.x, xS = c ? vS.y : vS.x;
+                    const double xC = c ? vC.y : vC.x;
+                    const double xW = c ? vC.x : vW0, xE = c ? vE1 : vC.y;
+                    const double A1 = first ? 0.0 : (lastq ? -(aN + aN) : -aN);
+                    const double A5 = lastq ? 0.0 : (first ? -(aS + aS) : -aS);
+                    const double A2 = firstc ? 0.0 : (lastc ? -(aW + aW) : -aW);
+                    const double A4 = lastc ? 0.0 : (firstc ? -(aE + aE) : -aE);
+                    const double A3 = c ? acC.y : acC.x;
+                    double y = A1 * xN;
+                    y = y + A2 * xW;
+                    y = y + A3 * xC;
+                    y = y + A4 * xE;
+                    y = y + A5 * xS;
+                    const bool valid = c ? valid1 : valid0;
+                    const double qq = valid ? y : 0.0;
+                    if (c) q2.y = qq; else q2.x = qq;
+                    acc0 += xC * qq;
+                    acc1 += valid ? xC * xC : 0.0;
+                }
+                st2(a.p + off, vC);
+                st2(a.q + off, q2);
+            }
+            vN = vC; vC = vS; dN = dC; dC = dS; acC = acS; veC = veS; deC = deS;
+        }
+        if (a.write_ghost_bot && i_end == g.rows && inrow) st2(a.p + off, vC);
+    }
+
+    const int nb = gridDim.x * gridDim.y;
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm)) {
+        if (a.fuse_scalars) scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace, a.hs);
+        else { S->part[0] = acc0; S->part[1] = acc1; }
     }
 }
 
@@ -559,11 +770,9 @@ __global__ void __launch_bounds__(256) k_mass(const MassArgs a) {
 
 // ---------------------------------------------------------------- launchers
 
-void kernel_config_from_env() {
-    if (const char *e = getenv("PDEODE_BS")) {
-        const int v = atoi(e);
-        if (v == 64 || v == 128 || v == 256) g_bs_stencil = v;
-    }
+static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+LaunchCfg launch_config(const GridDesc &g) {
     if (const char *e = getenv("PDEODE_STREAM_CTAS")) {
         const int v = atoi(e);
         if (v >= 1 && v <= 32) g_stream_ctas_per_sm = v;
@@ -572,11 +781,37 @@ void kernel_config_from_env() {
     if (cudaGetDevice(&dev) == cudaSuccess &&
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && sms > 0)
         g_num_sms = sms;
+
+    // Measured on B200 at 4096^2 (profiles/r01_sweep_*.txt): the bulk-async
+    // variant peaks at BS 256, depth 4, 64 rows per CTA.  Narrow grids take a
+    // narrower strip; short grids take fewer rows per CTA so that about two
+    // CTAs per SM exist.
+    LaunchCfg c;
+    c.variant = 1;
+    c.DEPTH = 4;
+    c.BS = (g.P <= 128) ? 64 : (g.P <= 256 ? 128 : 256);
+    const int nstrips = cdiv(g.P, 2 * c.BS);
+    const int want_chunks = cdiv(2 * g_num_sms, nstrips);
+    c.TR = g.rows / want_chunks;
+    if (c.TR > 64) c.TR = 64;
+    if (c.TR < 8) c.TR = 8;
+    if (const char *e = getenv("PDEODE_BS")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) c.BS = v;
+    }
+    if (const char *e = getenv("PDEODE_TR")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4096) c.TR = v;
+    }
+    if (const char *e = getenv("PDEODE_VARIANT")) c.variant = (e[0] == 'b') ? 1 : 0;   // bulk | reg
+    if (const char *e = getenv("PDEODE_DEPTH")) {
+        const int v = atoi(e);
+        if (v >= 2 && v <= 8) c.DEPTH = v;
+    }
+    return c;
 }
 
 int stream_blocks() { return g_num_sms * g_stream_ctas_per_sm; }
-
-static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 static int flat_blocks(long long n2) {
     const long long want = (n2 + 255) / 256;
@@ -597,7 +832,7 @@ cudaError_t launch_diffcoef(const GridDesc &g, const NumParams &np, const double
 
 template <int MODE>
 static cudaError_t launch_stencil(const StencilArgs &a, cudaStream_t st) {
-    const int bs = g_bs_stencil;
+    const int bs = a.BS;
     dim3 grid(cdiv(a.g.P, 2 * bs), cdiv(a.g.rows, a.TR));
     if (bs == 64) k_stencil<MODE, 64><<<grid, 64, 0, st>>>(a);
     else if (bs == 256) k_stencil<MODE, 256><<<grid, 256, 0, st>>>(a);
@@ -608,7 +843,39 @@ static cudaError_t launch_stencil(const StencilArgs &a, cudaStream_t st) {
 cudaError_t launch_stencil_init(const StencilArgs &a, cudaStream_t st) {
     return launch_stencil<MODE_INIT>(a, st);
 }
+template <int BS, int DEPTH>
+static cudaError_t launch_spmv_bulk(const StencilArgs &a, cudaStream_t st) {
+    constexpr int TC = 2 * BS, SEG = TC + 4;
+    constexpr size_t smem = (size_t)DEPTH * (3 * SEG + TC) * sizeof(double) + 2 * DEPTH * 8;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_spmv_bulk<BS, DEPTH>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(cdiv(a.g.P, TC), cdiv(a.g.rows, a.TR));
+    k_spmv_bulk<BS, DEPTH><<<grid, BS + 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stencil_cg(const StencilArgs &a, cudaStream_t st) {
+    if (a.variant == 1) {
+        const int bs = a.BS, dp = a.DEPTH;
+        if (bs == 256) {
+            if (dp <= 2) return launch_spmv_bulk<256, 2>(a, st);
+            if (dp <= 4) return launch_spmv_bulk<256, 4>(a, st);
+            return launch_spmv_bulk<256, 6>(a, st);
+        }
+        if (bs == 64) {
+            if (dp <= 4) return launch_spmv_bulk<64, 4>(a, st);
+            return launch_spmv_bulk<64, 8>(a, st);
+        }
+        if (dp <= 2) return launch_spmv_bulk<128, 2>(a, st);
+        if (dp <= 4) return launch_spmv_bulk<128, 4>(a, st);
+        if (dp <= 6) return launch_spmv_bulk<128, 6>(a, st);
+        return launch_spmv_bulk<128, 8>(a, st);
+    }
     return launch_stencil<MODE_CG>(a, st);
 }
 

@@ -49,9 +49,19 @@ def run(name):
     out = dict(row=row, col=col, M0=M0, C0=C0, steps=steps,
                over_keys=np.array(list(over.keys()), dtype="U16"),
                over_vals=np.array(list(over.values()), dtype=np.float64))
-    counts, nits, masses = [], [], []
+    # the same run with the OpenMP build: env[k] = how far the reference's two
+    # builds are from each other after step k+1 (its self-consistency envelope)
+    o2 = ol.Oracle(row, col, p, omp=True)
+    o2.set_state(M0, C0)
+    counts, nits, masses, env = [], [], [], []
     for k in range(steps):
         r = o.step()
+        o2.step()
+        Ma, Ca = o.get_state()
+        Mb, Cb = o2.get_state()
+        env.append(max(np.linalg.norm(Ma - Mb) / np.linalg.norm(Ma),
+                       np.linalg.norm(Ca - Cb) / np.linalg.norm(Ca)))
+        out["env"] = np.array(env)
         counts.append(r["countIters"])
         nits.append((r["nits"] + [0] * 16)[:16])
         M, C = o.get_state()
