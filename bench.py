@@ -35,7 +35,7 @@ FALLBACK_HBM_GBS = 6650.0      # /opt/skills/guides/B200_PROFILING.md
 def ic1(row, col, height, depth):
     """MinitialCond = 1 of the reference (PDE-ODEsolver.f90:279-288), C = 1 (:276)."""
     xDel = 1.0 / row
-    a = -height / depth ** 4
+    a = -height / ((depth * depth) * (depth * depth))
     t = np.arange(row, dtype=np.float64) * xDel
     f = a * ((t * t) * (t * t)) + height
     f = np.where(f <= 0, 0.0, f)

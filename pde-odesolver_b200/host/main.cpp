@@ -1,0 +1,25 @@
+// main.cpp -- the executable the run scripts call as ./a.out
+// (runAll.sh:7, twoDimension_runall.sh:7: `echo FILE.txt | ./a.out`).
+// Same stdin / console / output-file contract as `program cThermoPDEODE`
+// (PDE-ODEsolver.f90:20-175); the time step runs on the B200 through
+// libpdeode_b200.so.  Environment (never the parameter file, whose format is
+// fixed): PDEODE_DEVICE = CUDA device ordinal (default 0), PDEODE_SEED = seed
+// of the random initial conditions (default: clock, like init_random_seed.f90).
+#include <cstdlib>
+
+#include "pdeode_host.h"
+
+int main() {
+    pdeode_host::Stepper st{};
+    st.create = pdeode_create;
+    st.set_state = pdeode_set_state;
+    st.get_state = pdeode_get_state;
+    st.step = pdeode_step;
+    st.mass = pdeode_mass;
+    st.peak = pdeode_peak;
+    st.destroy = pdeode_destroy;
+    st.strerror_ = pdeode_strerror;
+    int device = 0;
+    if (const char *d = getenv("PDEODE_DEVICE")) device = atoi(d);
+    return pdeode_host::run_program(stdin, stdout, st, device, "");
+}

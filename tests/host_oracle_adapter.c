@@ -1,0 +1,83 @@
+/*
+ * host_oracle_adapter.c -- TEST INFRASTRUCTURE.  Implements the stepper table
+ * the host program expects (pdeode_host::Stepper: the C ABI's entry points)
+ * on top of the CPU oracle, so that the host logic (parameter file, cadences,
+ * console, output files) can be exercised end to end on a machine without a
+ * GPU.  Never linked into the product.
+ */
+#include <stdlib.h>
+
+#include "../include/pdeode_b200.h"
+#include "../oracle/pdeode_oracle.h"
+
+struct pdeode_ctx {
+    oracle_state *o;
+    int row, col;
+    long n;
+    double *M, *C;
+};
+
+static int a_create(pdeode_ctx **out, int row, int col, const pdeode_params *p, int device)
+{
+    (void)device;
+    pdeode_ctx *c = (pdeode_ctx *)calloc(1, sizeof(*c));
+    if (!c) return PDEODE_ERR_NOMEM;
+    c->o = oracle_create(row, col, (const oracle_params *)p);   /* identical layout */
+    c->row = row; c->col = col; c->n = (long)row * col;
+    c->M = (double *)malloc(sizeof(double) * c->n);
+    c->C = (double *)malloc(sizeof(double) * c->n);
+    if (!c->o || !c->M || !c->C) return PDEODE_ERR_NOMEM;
+    *out = c;
+    return PDEODE_OK;
+}
+static int a_set_state(pdeode_ctx *c, const double *M, const double *C)
+{
+    oracle_set_state(c->o, M, C);
+    return PDEODE_OK;
+}
+static int a_get_state(pdeode_ctx *c, double *M, double *C)
+{
+    oracle_get_state(c->o, M, C);
+    return PDEODE_OK;
+}
+static int a_step(pdeode_ctx *c, int *cnt, long long *sum, long long *mx)
+{
+    return oracle_step(c->o, cnt, sum, mx, NULL, NULL, 0) ? PDEODE_ERR_PICARD_CAP : PDEODE_OK;
+}
+static int a_mass(pdeode_ctx *c, double *mM, double *mC)
+{
+    oracle_get_state(c->o, c->M, c->C);
+    *mM = oracle_calc_mass(c->M, c->n);
+    *mC = oracle_calc_mass(c->C, c->n);
+    return PDEODE_OK;
+}
+static int a_peak(pdeode_ctx *c, double *peak, double *height, double *intfac)
+{
+    oracle_get_state(c->o, c->M, c->C);
+    oracle_calc_peak_interface(c->M, c->row, c->col, peak, height, intfac);
+    return PDEODE_OK;
+}
+static int a_destroy(pdeode_ctx *c)
+{
+    if (!c) return PDEODE_OK;
+    oracle_destroy(c->o);
+    free(c->M); free(c->C); free(c);
+    return PDEODE_OK;
+}
+static const char *a_strerror(int code) { return code ? "oracle adapter error" : "ok"; }
+
+typedef struct {
+    int (*create)(pdeode_ctx **, int, int, const pdeode_params *, int);
+    int (*set_state)(pdeode_ctx *, const double *, const double *);
+    int (*get_state)(pdeode_ctx *, double *, double *);
+    int (*step)(pdeode_ctx *, int *, long long *, long long *);
+    int (*mass)(pdeode_ctx *, double *, double *);
+    int (*peak)(pdeode_ctx *, double *, double *, double *);
+    int (*destroy)(pdeode_ctx *);
+    const char *(*strerror_)(int);
+} stepper_table;
+
+static const stepper_table TABLE = {a_create, a_set_state, a_get_state, a_step,
+                                    a_mass,   a_peak,      a_destroy,   a_strerror};
+
+const void *oracle_stepper_table(void) { return &TABLE; }

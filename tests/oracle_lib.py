@@ -169,7 +169,7 @@ def ic1(row, col, height, depth):
     """MinitialCond = 1 (P:279-288): M = max(0, a*(x*xDel)^4 + height),
     x = (i-1)/col (row index), a = -height/depth^4; C = 1 (P:276)."""
     xDel = 1.0 / row
-    a = -height / depth ** 4
+    a = -height / ((depth * depth) * (depth * depth))     # (depth)**4 as gfortran expands it
     x = np.arange(row, dtype=np.float64)
     xx = x * xDel
     f = a * ((xx * xx) * (xx * xx)) + height

@@ -1,0 +1,71 @@
+"""The host program on the GPU (`echo FILE | pdeode_solver`, what the run scripts
+call as ./a.out) against the same host logic driven by the CPU oracle."""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import __graft_entry__ as ge
+import oracle_lib as ol
+from test_host_program import DATA, split_frames
+
+pytestmark = pytest.mark.gpu
+
+
+def run_oracle_program(param, outdir, console):
+    from test_host_program import BUILD, HERE
+    os.makedirs(BUILD, exist_ok=True)
+    so = os.path.join(BUILD, "libhost_oracle_adapter.so")
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", so,
+                           os.path.join(HERE, "host_oracle_adapter.c"),
+                           "-L" + ol.ORACLE_DIR, "-loracle", "-Wl,-rpath," + ol.ORACLE_DIR])
+    ad = C.CDLL(so)
+    ad.oracle_stepper_table.restype = C.c_void_p
+    host = C.CDLL(os.path.join(ge.LIBDIR, "libpdeode_hostlogic.so"))
+    host.pdeode_host_run.argtypes = [C.c_char_p, C.c_char_p, C.c_char_p, C.c_void_p, C.c_int]
+    return host.pdeode_host_run(param.encode(), outdir.encode(), console.encode(),
+                                ad.oracle_stepper_table(), 0)
+
+
+@pytest.mark.parametrize("name,frame_file", [("wave2d.txt", "2D_output.dat"), ("square3d.txt", "output.dat")])
+def test_solver_binary_matches_oracle_driven_host(tmp_path, name, frame_file):
+    ge.build_cuda(); ge.build_host(); ol.build_oracle()
+    param = os.path.join(DATA, name)
+    gdir = tmp_path / "gpu"; odir = tmp_path / "cpu"
+    gdir.mkdir(); odir.mkdir()
+    exe = os.path.join(ge.BINDIR, "pdeode_solver")
+    r = subprocess.run([exe], input=param + "\n", text=True, capture_output=True, cwd=gdir,
+                       env=dict(os.environ, PDEODE_SEED="1"), timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert run_oracle_program(param, str(odir), str(tmp_path / "cpu_console.txt")) == 0
+    assert sorted(os.listdir(gdir)) == sorted(os.listdir(odir))
+    for f in ("total.dat", "COprod.dat") + (("peakInfo.dat",) if frame_file.startswith("2D") else ()):
+        a, b = np.loadtxt(gdir / f), np.loadtxt(odir / f)
+        assert a.shape == b.shape
+        assert np.allclose(a, b, rtol=2e-7, atol=1e-12), f
+    fa, fb = split_frames(str(gdir / frame_file)), split_frames(str(odir / frame_file))
+    assert len(fa) == len(fb)
+    for x, y in zip(fa, fb):
+        xa = np.array([[float(v) for v in l.split()] for l in x if l.strip()])
+        ya = np.array([[float(v) for v in l.split()] for l in y if l.strip()])
+        assert xa.shape == ya.shape
+        if xa.size:
+            assert np.allclose(xa, ya, rtol=2e-7, atol=1e-12)
+    # console: same text up to the timing line and the statistics digits
+    gl = r.stdout.splitlines()
+    ol_ = open(tmp_path / "cpu_console.txt").read().splitlines()
+    assert len(gl) == len(ol_)
+    hdr = next(i for i, l in enumerate(gl) if "avgIter" in l)
+    assert gl[:hdr + 1] == ol_[:hdr + 1]
+    for a, b in zip(gl[hdr + 1:], ol_[hdr + 1:]):
+        if "Time to compute" in a:
+            continue
+        ta, tb = a.split(), b.split()
+        assert len(ta) == len(tb)
+        for u, v in zip(ta, tb):
+            try:
+                assert float(u) == pytest.approx(float(v), rel=5e-2, abs=1e-6)
+            except ValueError:
+                assert u == v
