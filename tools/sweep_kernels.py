@@ -26,8 +26,8 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--grid", type=int, default=4096)
     ap.add_argument("--reps", type=int, default=30)
-    ap.add_argument("--bs", default="128")
-    ap.add_argument("--tr", default="16")
+    ap.add_argument("--bs", default="0")
+    ap.add_argument("--tr", default="0")
     ap.add_argument("--variant", default="")
     ap.add_argument("--kernels", default="cg_spmv,cg_update")
     args = ap.parse_args()
@@ -41,10 +41,12 @@ def main():
     for var in variants:
         for bs in args.bs.split(","):
             for tr in args.tr.split(","):
-                os.environ["PDEODE_BS"] = bs
-                os.environ["PDEODE_TR"] = tr
-                if var:
-                    os.environ["PDEODE_VARIANT"] = var
+                # "0" = leave the library's own heuristic in charge
+                for key, val in (("PDEODE_BS", bs), ("PDEODE_TR", tr), ("PDEODE_VARIANT", var)):
+                    if val and val != "0":
+                        os.environ[key] = val
+                    else:
+                        os.environ.pop(key, None)
                 s = pb.Solver(row, col, pb.default_params(row, eSoln=1.5))
                 s.set_state(M0, C0)
                 s.set_maxit(3)
