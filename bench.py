@@ -236,6 +236,7 @@ def main():
     n = row * col
     params = pb.default_params(row)
     s = pb.Solver(row, col, params, device=local, rank=rank, nranks=world, nccl_id=nccl_id)
+    exchange = s.exchange_mode()
     stream = torch.cuda.Stream()           # the library launches here; events are recorded here
     s.set_stream(stream.cuda_stream)
     s.set_maxit(args.cg_cap)               # safety net only; a hit invalidates the run (checked below)
@@ -352,6 +353,10 @@ def main():
 
     if rank == 0:
         cfg = workload_config(args, world)
+        cfg["exchange"] = {"single": "none (one GPU)",
+                           "nccl": "NCCL send/recv of one ghost row + 2 all-reduces per CG iteration",
+                           "peer": "inside K_A/K_B over NVLink peer memory (CUDA IPC): ghost rows and "
+                                   "dot-product slots written straight into the other GPUs"}[exchange]
         if default_ms:
             cfg["shipped_parameters_run"] = default_ms
         out = {

@@ -139,6 +139,11 @@ int pdeode_cg_trace_get(pdeode_ctx *ctx, double *out, int cap, int *count);
 #define PDEODE_ARR_Q     7
 int pdeode_debug_get_array(pdeode_ctx *ctx, int which, double *out);
 
+/* How this context exchanges ghost rows and dot products per CG iteration:
+ * 0 = single GPU (nothing to exchange), 1 = NCCL send/recv + all-reduce,
+ * 2 = inside the CG kernels over NVLink peer memory (CUDA-IPC mappings). */
+int pdeode_exchange_mode(const pdeode_ctx *ctx, int *mode);
+
 /* Kernels launched by this context so far. */
 int pdeode_launch_count(const pdeode_ctx *ctx, long long *launches);
 

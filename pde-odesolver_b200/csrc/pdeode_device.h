@@ -58,6 +58,33 @@ struct DevScal {
     int trace_cap, trace_len;
     // tickets for the last-block-done reductions
     unsigned int ticket[8];
+    int error;           // 1: a peer exchange timed out (multi-rank peer mode)
+    int pad2;
+};
+
+// How a kernel's reduction leaves the grid (StencilArgs / UpdateArgs ::fuse_scalars).
+enum {
+    SUMS_RAW = 0,    // rank-local sums into DevScal::part; NCCL all-reduce + a scalar kernel follow
+    SUMS_FUSED = 1,  // single rank: the last CTA turns the sums into alfa / beta / stop itself
+    SUMS_PEER = 2    // multi rank: the last CTA stores the sums into every rank's comm block over
+                     // NVLink; the next kernel's CTAs wait for all ranks' flags and add the slots
+};
+
+constexpr int PEER_MAX_RANKS = 8;
+constexpr int PEER_SLOTS = 4;    // phases in flight never span more than two slots
+
+// Peer-memory exchange of one context (multi rank).  Every rank owns a comm
+// block {slots[PEER_SLOTS][PEER_MAX_RANKS][2], flags[PEER_SLOTS][PEER_MAX_RANKS]}
+// that the other ranks write into through CUDA-IPC mappings; r_up / r_dn are the
+// neighbours' residual arrays, whose ghost rows this rank fills directly.
+struct PeerComm {
+    int rank, nranks;
+    const double *slots;                       // local comm block, written by peers
+    const unsigned long long *flags;
+    double *peer_slots[PEER_MAX_RANKS];        // every rank's comm block (self included)
+    unsigned long long *peer_flags[PEER_MAX_RANKS];
+    double *r_up, *r_dn;                       // origin (row 0, col 0) of the neighbours' r, or null
+    int rows_up;                               // local rows of rank-1 (its bottom ghost row index)
 };
 
 struct HostStatus {           // written by the device into mapped host memory
@@ -86,9 +113,11 @@ struct StencilArgs {
     int BS;                // consumer threads per CTA (64 | 128 | 256); strip = 2*BS columns
     int DEPTH;             // ring depth in rows of the bulk-async variant
     int variant;           // CG SpMV: 0 register-staged, 1 bulk-async staged (default)
-    int fuse_scalars;      // 1: last block turns sums into alfa/stop (single rank)
+    int fuse_scalars;      // SUMS_RAW | SUMS_FUSED | SUMS_PEER
     int write_ghost_top, write_ghost_bot; // maintain p ghost rows (multi rank)
     long long seq;
+    PeerComm pc;           // SUMS_PEER only
+    unsigned long long wait_phase, post_phase;
 };
 
 struct UpdateArgs {
@@ -101,6 +130,10 @@ struct UpdateArgs {
     long long n2;          // number of double2 elements to stream (rows*P/2)
     int fuse_scalars;
     long long seq;
+    NumParams np;          // SUMS_PEER: the stop test runs in this kernel's last CTA
+    double *trace;
+    PeerComm pc;
+    unsigned long long wait_phase, post_phase;
 };
 
 struct SolveCArgs {

@@ -62,6 +62,14 @@ struct pdeode_ctx {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     ncclComm_t comm = nullptr;
 
+    // peer-memory exchange (multi rank): see PeerComm in pdeode_device.h
+    bool peer = false;
+    PeerComm pc{};
+    void *comm_block = nullptr;                 // this rank's slots + flags
+    void *ipc_open[2 * PEER_MAX_RANKS + 2] = {nullptr};
+    int n_ipc_open = 0;
+    unsigned long long phase = 0;               // id of the last posting kernel launched
+
     LaunchCfg cfg{256, 64, 4, 1};
     int pred[MAX_PICARD_TRACE];
     long long seq = 0;
@@ -110,6 +118,9 @@ int fail_nccl(pdeode_ctx *c, int e, const char *what) {
     } while (0)
 
 inline bool multi(const pdeode_ctx *c) { return c->nranks > 1; }
+inline int sums_mode(const pdeode_ctx *c) {
+    return !multi(c) ? SUMS_FUSED : (c->peer ? SUMS_PEER : SUMS_RAW);
+}
 
 // ghost-row exchange with the slabs above and below (one row each way)
 int halo_exchange(pdeode_ctx *c, double *X) {
@@ -155,7 +166,8 @@ StencilArgs stencil_args(pdeode_ctx *c) {
     a.d = c->d; a.ac = c->ac; a.r = c->r; a.q = c->q;
     a.p_in = c->pbuf[c->ip]; a.p = c->pbuf[c->ip ^ 1];
     a.TR = c->cfg.TR; a.BS = c->cfg.BS; a.DEPTH = c->cfg.DEPTH; a.variant = c->cfg.variant;
-    a.fuse_scalars = multi(c) ? 0 : 1;
+    a.fuse_scalars = sums_mode(c);
+    a.pc = c->pc;
     a.write_ghost_top = multi(c) && c->rank > 0;
     a.write_ghost_bot = multi(c) && c->rank < c->nranks - 1;
     a.seq = c->seq;
@@ -164,12 +176,15 @@ StencilArgs stencil_args(pdeode_ctx *c) {
 
 // one CG iteration: CG:55-90
 int cg_iteration(pdeode_ctx *c, double *x) {
+    const int mode = sums_mode(c);
     StencilArgs a = stencil_args(c);
+    a.wait_phase = c->phase;                 // posted by INIT or the previous K_B
+    a.post_phase = ++c->phase;
     CK(launch_stencil_cg(a, c->stream));
     c->launches++;
     c->ip ^= 1;                      // the direction just written is the current one
     c->p = c->pbuf[c->ip];
-    if (multi(c)) {
+    if (mode == SUMS_RAW) {
         int rc = allreduce_part(c, 2);
         if (rc) return rc;
         CK(launch_scal_after_spmv(c->S, c->g, c->np.tol2, a.trace, nullptr, c->seq, c->stream));
@@ -179,11 +194,14 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     u.g = c->g; u.S = c->S; u.partials = c->partials; u.hs = nullptr;
     u.x = x; u.r = c->r; u.p = c->p; u.q = c->q;
     u.n2 = (long long)c->g.rows * c->g.P / 2;
-    u.fuse_scalars = multi(c) ? 0 : 1;
+    u.fuse_scalars = mode;
     u.seq = c->seq;
+    u.np = c->np; u.trace = a.trace; u.pc = c->pc;
+    u.wait_phase = c->phase;                 // posted by the K_A just launched
+    u.post_phase = ++c->phase;
     CK(launch_update(u, c->stream));
     c->launches++;
-    if (multi(c)) {
+    if (mode == SUMS_RAW) {
         int rc = allreduce_part(c, 2);
         if (rc) return rc;
         CK(launch_scal_after_update(c->S, nullptr, c->seq, c->stream));
@@ -204,9 +222,10 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     }
     StencilArgs a = stencil_args(c);
     a.x0 = x0; a.x = x; a.Cc = c->Cb[c->iC]; a.Mprev = c->Mb[c->iMprev];
+    a.post_phase = ++c->phase;
     CK(launch_stencil_init(a, c->stream));
     c->launches++;
-    if (multi(c)) {
+    if (sums_mode(c) == SUMS_RAW) {
         int rc = allreduce_part(c, 2);
         if (rc) return rc;
         CK(launch_scal_after_init(c->S, c->stream));
@@ -257,6 +276,10 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         chunk = (int)std::min<long long>(std::max<long long>(2, launched / 2), 1024);
     }
     const DevScal &fin = c->snap[slot].s;
+    if (fin.error) {
+        c->err = "peer exchange timed out (a rank stopped posting)";
+        return PDEODE_ERR_CUDA;
+    }
     // launches after convergence were no-ops: the direction of the last real
     // iteration sits in the buffer given by the parity of nit
     c->ip = ip0 ^ (int)(fin.nit & 1);
@@ -335,6 +358,78 @@ void set_numparams(pdeode_ctx *c, const pdeode_params *p) {
     n.dSelect = p->dSelect; n.fSelect = p->fSelect; n.gSelect = p->gSelect;
 }
 
+// Maps every rank's comm block and the two neighbours' residual arrays into
+// this process (CUDA IPC over NVLink) so that K_A / K_B exchange their sums and
+// ghost rows themselves.  If the mappings cannot be made on every rank the
+// context stays on the NCCL path; the decision is taken collectively.
+int setup_peer(pdeode_ctx *c) {
+    struct Desc {
+        cudaIpcMemHandle_t comm, r;
+        int rows, ok;
+    };
+    const int nr = c->nranks;
+    const size_t slots_bytes = sizeof(double) * PEER_SLOTS * PEER_MAX_RANKS * 2;
+    const size_t flags_bytes = sizeof(unsigned long long) * PEER_SLOTS * PEER_MAX_RANKS;
+    CK(cudaMalloc(&c->comm_block, slots_bytes + flags_bytes));
+    CK(cudaMemset(c->comm_block, 0, slots_bytes + flags_bytes));
+    Desc mine{};
+    mine.rows = c->g.rows;
+    mine.ok = (cudaIpcGetMemHandle(&mine.comm, c->comm_block) == cudaSuccess &&
+               cudaIpcGetMemHandle(&mine.r, c->base[8]) == cudaSuccess);
+    cudaGetLastError();
+    Desc *dall = nullptr;
+    CK(cudaMalloc(&dall, sizeof(Desc) * (size_t)nr));
+    CK(cudaMemcpy(dall + c->rank, &mine, sizeof(Desc), cudaMemcpyHostToDevice));
+    NK(nccl().AllGather(dall + c->rank, dall, sizeof(Desc), NCCL_INT8, c->comm, c->stream));
+    std::vector<Desc> all((size_t)nr);
+    CK(cudaMemcpyAsync(all.data(), dall, sizeof(Desc) * (size_t)nr, cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    CK(cudaFree(dall));
+
+    bool ok = true;
+    for (int r = 0; r < nr; ++r) ok = ok && all[(size_t)r].ok;
+    PeerComm pc{};
+    pc.rank = c->rank; pc.nranks = nr;
+    pc.slots = (const double *)c->comm_block;
+    pc.flags = (const unsigned long long *)((char *)c->comm_block + slots_bytes);
+    const size_t origin = (size_t)GUARD + (size_t)c->g.P;        // (row 0, col 0) inside an array
+    for (int r = 0; r < nr && ok; ++r) {
+        void *cb = c->comm_block;
+        if (r != c->rank) {
+            if (cudaIpcOpenMemHandle(&cb, all[(size_t)r].comm, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = false; cudaGetLastError(); break;
+            }
+            c->ipc_open[c->n_ipc_open++] = cb;
+        }
+        pc.peer_slots[r] = (double *)cb;
+        pc.peer_flags[r] = (unsigned long long *)((char *)cb + slots_bytes);
+        if (r == c->rank - 1 || r == c->rank + 1) {
+            void *rb = nullptr;
+            if (cudaIpcOpenMemHandle(&rb, all[(size_t)r].r, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) {
+                ok = false; cudaGetLastError(); break;
+            }
+            c->ipc_open[c->n_ipc_open++] = rb;
+            if (r == c->rank - 1) { pc.r_up = (double *)rb + origin; pc.rows_up = all[(size_t)r].rows; }
+            else pc.r_dn = (double *)rb + origin;
+        }
+    }
+    // every rank must take the same path: all-reduce the verdict (sum of failures)
+    double *flag = c->gather;
+    const double bad = ok ? 0.0 : 1.0;
+    CK(cudaMemcpy(flag, &bad, sizeof(double), cudaMemcpyHostToDevice));
+    NK(nccl().AllReduce(flag, flag, 1, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream));
+    double nbad = 0.0;
+    CK(cudaMemcpyAsync(&nbad, flag, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    if (nbad == 0.0) {
+        c->pc = pc;
+        c->peer = true;
+    } else {
+        c->err = "CUDA IPC peer mapping unavailable; using the NCCL exchange";
+    }
+    return PDEODE_OK;
+}
+
 int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int device, int rank,
                 int nranks, const void *id) {
     if (!out) return PDEODE_ERR_ARG;
@@ -397,6 +492,11 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
         memcpy(&uid, id, sizeof uid);
         NK(nccl().CommInitRank(&c->comm, nranks, uid, rank));
         CK(cudaMalloc(&c->gather, sizeof(double) * 8 * (size_t)nranks));
+        const char *pe = getenv("PDEODE_PEER");
+        if (!(pe && pe[0] == '0') && nranks <= PEER_MAX_RANKS && c->cfg.variant == 1) {
+            int rc = setup_peer(c);
+            if (rc) return rc;
+        }
     }
     return PDEODE_OK;
 }
@@ -445,6 +545,13 @@ int pdeode_destroy(pdeode_ctx *c) {
     if (!c) return PDEODE_OK;
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
+    if (c->peer && c->comm && c->gather) {
+        // collective: no rank unmaps or frees memory a peer may still be writing into
+        nccl().AllReduce(c->gather, c->gather, 1, NCCL_DOUBLE, NCCL_SUM, c->comm, c->stream);
+        cudaStreamSynchronize(c->stream);
+    }
+    for (int k = 0; k < c->n_ipc_open; ++k) cudaIpcCloseMemHandle(c->ipc_open[k]);
+    if (c->comm_block) cudaFree(c->comm_block);
     if (c->comm) nccl().CommDestroy(c->comm);
     for (int k = 0; k < pdeode_ctx::NARR; ++k) if (c->base[k]) cudaFree(c->base[k]);
     if (c->partials) cudaFree(c->partials);
@@ -663,6 +770,12 @@ int pdeode_debug_get_array(pdeode_ctx *c, int which, double *out) {
     int rc = download(c, out, src);
     if (rc) return rc;
     CK(cudaStreamSynchronize(c->stream));
+    return PDEODE_OK;
+}
+
+int pdeode_exchange_mode(const pdeode_ctx *c, int *mode) {
+    if (!c || !mode) return PDEODE_ERR_ARG;
+    *mode = !multi(c) ? 0 : (c->peer ? 2 : 1);
     return PDEODE_OK;
 }
 

@@ -100,8 +100,12 @@ __device__ __forceinline__ void block_sum2(double &a, double &b, double *sm) {
 // CTA that draws the last ticket adds all partials in a fixed order.  Returns
 // true in thread 0 of that last CTA with (a, b) = grid totals.
 __device__ __forceinline__ bool grid_sum2(double &a, double &b, double *partials, int nb,
-                                          int bid, unsigned int *ticket, double *sm) {
+                                          int bid, unsigned int *ticket, double *sm,
+                                          bool sysfence = false) {
     __shared__ int s_last;
+    // peer mode: this CTA may have stored ghost rows into a neighbour GPU; they
+    // must be visible system-wide before the last CTA raises the flag
+    if (sysfence) __threadfence_system();
     block_sum2(a, b, sm);
     if (threadIdx.x == 0) {
         partials[bid] = a;
@@ -194,6 +198,69 @@ __global__ void k_scal_after_update(DevScal *S, HostStatus *hs, long long seq) {
 }
 __global__ void k_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq) {
     scal_after_solvec(S, S->part[0], S->part[1], g.n_glob, hs, seq);
+}
+
+// ---------------------------------------------------------------- peer-memory exchange
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+
+// All threads of the CTA call this.  Thread 0 waits until every rank has
+// posted `phase` into this rank's comm block, then adds the posted pairs in
+// rank order (the same order on every rank, so every rank gets the same bits).
+// A peer that never posts (crashed) makes the wait give up after ~1 s of GPU
+// clocks and raise DevScal::error instead of hanging the device.
+__device__ __forceinline__ void peer_wait_sums(const PeerComm &pc, unsigned long long phase,
+                                               DevScal *S, double &s0, double &s1) {
+    __shared__ double sh[2];
+    if (threadIdx.x == 0) {
+        const int slot = (int)(phase % PEER_SLOTS);
+        const unsigned long long *f = pc.flags + slot * PEER_MAX_RANKS;
+        const double *v = pc.slots + (size_t)slot * PEER_MAX_RANKS * 2;
+        const long long t0 = clock64();
+        bool ok = true;
+        for (int r = 0; r < pc.nranks && ok; ++r) {
+            while (ld_acquire_sys(f + r) < phase) {
+                if (clock64() - t0 > 2000000000LL) { ok = false; break; }
+            }
+        }
+        double a = 0.0, b = 0.0;
+        for (int r = 0; r < pc.nranks; ++r) {
+            a += ld_relaxed_sys(v + 2 * r);
+            b += ld_relaxed_sys(v + 2 * r + 1);
+        }
+        if (!ok) S->error = 1;
+        sh[0] = a; sh[1] = b;
+    }
+    __syncthreads();
+    s0 = sh[0]; s1 = sh[1];
+    __syncthreads();
+}
+
+// One thread: store this rank's pair into every rank's comm block, then raise
+// the flag there.  Ghost rows written earlier by other CTAs of this grid are
+// ordered before the flag by their own system fences (grid_sum2).
+__device__ __forceinline__ void peer_post(const PeerComm &pc, unsigned long long phase, double a,
+                                          double b) {
+    const int slot = (int)(phase % PEER_SLOTS);
+    for (int r = 0; r < pc.nranks; ++r) {
+        double *v = pc.peer_slots[r] + ((size_t)slot * PEER_MAX_RANKS + pc.rank) * 2;
+        v[0] = a; v[1] = b;
+    }
+    __threadfence_system();
+    for (int r = 0; r < pc.nranks; ++r)
+        st_release_sys(pc.peer_flags[r] + slot * PEER_MAX_RANKS + pc.rank, phase);
 }
 
 // ---------------------------------------------------------------- D(M)
@@ -373,6 +440,12 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
                 st2(a.ac + off, ac2);
                 st2(a.r + off, q2);
                 if (a.x != a.x0) st2(a.x + off, vC);
+                if (a.fuse_scalars == SUMS_PEER) {
+                    // my boundary rows of r are the neighbours' ghost rows
+                    if (i == 0 && a.pc.r_up)
+                        st2(a.pc.r_up + (long long)a.pc.rows_up * g.P + j0, q2);
+                    if (i == g.rows - 1 && a.pc.r_dn) st2(a.pc.r_dn - g.P + j0, q2);
+                }
             } else {
                 st2(a.p + off, vC);
                 st2(a.q + off, q2);
@@ -385,10 +458,16 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
 
     const int nb = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-    if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm)) {
-        if (a.fuse_scalars) {
+    if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm,
+                  a.fuse_scalars == SUMS_PEER)) {
+        if (a.fuse_scalars == SUMS_FUSED) {
             if (MODE == MODE_INIT) scal_after_init(S, acc0, acc1);
             else scal_after_spmv(S, acc0, acc1, g.n_glob, np.tol2, a.trace, a.hs);
+        } else if (a.fuse_scalars == SUMS_PEER && MODE == MODE_INIT) {
+            // rho and sum(sol*sol) become known to every rank once all have posted; the
+            // first K_A adds the slots.  Local part of CG:53 happens here.
+            scal_after_init(S, 0.0, 0.0);
+            peer_post(a.pc, a.post_phase, acc0, acc1);
         } else {
             S->part[0] = acc0; S->part[1] = acc1;
         }
@@ -460,7 +539,15 @@ __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
     DevScal *S = a.S;
     if (S->done) return;
     const bool firstit = (S->nit == 0);
-    const double beta = firstit ? 0.0 : S->rho / S->rho_old;       // CG:68
+    double beta, rr_glob = 0.0, xx_glob = 0.0;
+    if (a.fuse_scalars == SUMS_PEER) {
+        // dotProd(r,r) and sum(sol*sol) of the previous phase arrive from all ranks;
+        // the neighbours' flags also cover the ghost rows of r they wrote here
+        peer_wait_sums(a.pc, a.wait_phase, S, rr_glob, xx_glob);
+        beta = firstit ? 0.0 : rr_glob / S->rho;                   // S->rho still holds rho_old
+    } else {
+        beta = firstit ? 0.0 : S->rho / S->rho_old;                // CG:68
+    }
     const GridDesc g = a.g;
     const int tid = threadIdx.x;
     const int jt = blockIdx.x * TC;                 // first column of the strip
@@ -601,9 +688,18 @@ __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
 
     const int nb = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-    if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm)) {
-        if (a.fuse_scalars) scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace, a.hs);
-        else { S->part[0] = acc0; S->part[1] = acc1; }
+    if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm,
+                  a.fuse_scalars == SUMS_PEER)) {
+        if (a.fuse_scalars == SUMS_FUSED) {
+            scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace, a.hs);
+        } else if (a.fuse_scalars == SUMS_PEER) {
+            // close the previous phase (CG:56,57,59) now that every CTA has used rho_old,
+            // then hand this rank's p.q and p.p to all ranks
+            S->rho_old = S->rho; S->rho = rr_glob; S->xx = xx_glob;
+            peer_post(a.pc, a.post_phase, acc0, acc1);
+        } else {
+            S->part[0] = acc0; S->part[1] = acc1;
+        }
     }
 }
 
@@ -616,7 +712,23 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     __shared__ double sm[64];
     DevScal *S = a.S;
     if (S->finished) return;
-    const double alfa = S->alfa;
+    const bool peer = (a.fuse_scalars == SUMS_PEER);
+    double alfa, pq_glob = 0.0, pp_glob = 0.0;
+    if (peer) {
+        peer_wait_sums(a.pc, a.wait_phase, S, pq_glob, pp_glob);   // dotProd(p,q), sum(p*p)
+        alfa = S->rho / pq_glob;                                   // CG:77
+    } else {
+        alfa = S->alfa;
+    }
+    // peer mode: rows 0 and rows-1 of r are also the neighbours' ghost rows
+    const long long last_row0 = (long long)(a.g.rows - 1) * a.g.P;
+    double *const up = peer && a.pc.r_up ? a.pc.r_up + (long long)a.pc.rows_up * a.g.P : nullptr;
+    double *const dn = peer && a.pc.r_dn ? a.pc.r_dn - a.g.P - last_row0 : nullptr;
+    auto put_r = [&](long long k, double2 v) {
+        st2(a.r + k, v);
+        if (up && k < a.g.P) st2(up + k, v);
+        if (dn && k >= last_row0) st2(dn + k, v);
+    };
     double rr = 0.0, xx = 0.0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -628,8 +740,8 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
         x1.x = x1.x + alfa * p1.x; x1.y = x1.y + alfa * p1.y;
         r1.x = r1.x - alfa * q1.x; r1.y = r1.y - alfa * q1.y;
-        st2(a.x + k0, x0); st2(a.r + k0, r0);
-        st2(a.x + k1, x1); st2(a.r + k1, r1);
+        st2(a.x + k0, x0); put_r(k0, r0);
+        st2(a.x + k1, x1); put_r(k1, r1);
         rr += r0.x * r0.x; rr += r0.y * r0.y; rr += r1.x * r1.x; rr += r1.y * r1.y;
         xx += x0.x * x0.x; xx += x0.y * x0.y; xx += x1.x * x1.x; xx += x1.y * x1.y;
     }
@@ -638,13 +750,22 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         double2 x0 = ld2(a.x + k0), p0 = ld2(a.p + k0), r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
         x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
         r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
-        st2(a.x + k0, x0); st2(a.r + k0, r0);
+        st2(a.x + k0, x0); put_r(k0, r0);
         rr += r0.x * r0.x; rr += r0.y * r0.y;
         xx += x0.x * x0.x; xx += x0.y * x0.y;
     }
-    if (grid_sum2(rr, xx, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_UPDATE], sm)) {
-        if (a.fuse_scalars) scal_after_update(S, rr, xx, a.hs, a.seq);
-        else { S->part[0] = rr; S->part[1] = xx; }
+    if (grid_sum2(rr, xx, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_UPDATE], sm, peer)) {
+        if (a.fuse_scalars == SUMS_FUSED) {
+            scal_after_update(S, rr, xx, a.hs, a.seq);
+        } else if (peer) {
+            // the stop test of this iteration (CG:55,77,87-90) with the all-rank sums, then
+            // this rank's dotProd(r,r) and sum(sol*sol) go to all ranks
+            scal_after_spmv(S, pq_glob, pp_glob, a.g.n_glob, a.np.tol2, a.trace, nullptr);
+            S->finished = S->done;
+            peer_post(a.pc, a.post_phase, rr, xx);
+        } else {
+            S->part[0] = rr; S->part[1] = xx;
+        }
     }
 }
 

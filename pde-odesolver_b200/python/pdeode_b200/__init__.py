@@ -84,6 +84,7 @@ def _lib():
         "pdeode_cg_trace_get": [vp, dp, C.c_int, ip],
         "pdeode_debug_get_array": [vp, C.c_int, vp],
         "pdeode_launch_count": [vp, llp],
+        "pdeode_exchange_mode": [vp, ip],
         "pdeode_time_kernel": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
         "pdeode_kernel_bytes_per_cell": [C.c_int],
     }
@@ -228,6 +229,11 @@ class Solver:
         out = np.empty(self.n_local)
         self._ck(self.lib.pdeode_debug_get_array(self.h, which, _ptr(out)), "debug_get_array")
         return out
+
+    def exchange_mode(self):
+        v = C.c_int()
+        self._ck(self.lib.pdeode_exchange_mode(self.h, C.byref(v)), "exchange_mode")
+        return {0: "single", 1: "nccl", 2: "peer"}[v.value]
 
     def launch_count(self):
         v = C.c_longlong()

@@ -53,6 +53,8 @@ def main():
         ref = pb.Solver(row, col, p, device=local)
         ref.set_state(M0, C0)
     ok = True
+    if rank == 0:
+        print("exchange mode:", s.exchange_mode(), flush=True)
     for k in range(args.steps):
         g = s.step_trace()
         mass = s.mass()
