@@ -78,6 +78,10 @@ int pdeode_nccl_unique_id(void *id_out);
 
 int pdeode_destroy(pdeode_ctx *ctx);
 
+/* The row-slab partition itself (no device needed): rank's rows of a `row`-row
+ * grid split over nranks. */
+int pdeode_slab_rows(int row, int nranks, int rank, int *row0, int *nrows);
+
 /* Global rows owned by this context: [*row0, *row0 + *nrows). */
 int pdeode_local_rows(const pdeode_ctx *ctx, int *row0, int *nrows);
 

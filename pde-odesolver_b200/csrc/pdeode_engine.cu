@@ -447,9 +447,9 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     c->device = device; c->rank = rank; c->nranks = nranks; c->params = *p;
     CK(cudaSetDevice(device));
 
-    const int r0 = (int)((long long)rank * row / nranks);
-    const int r1 = (int)((long long)(rank + 1) * row / nranks);
-    c->g.rows = r1 - r0; c->g.col = col; c->g.P = (col + 15) / 16 * 16;
+    int r0 = 0, nrows_local = 0;
+    pdeode_slab_rows(row, nranks, rank, &r0, &nrows_local);
+    c->g.rows = nrows_local; c->g.col = col; c->g.P = (col + 15) / 16 * 16;
     c->g.row0 = r0; c->g.grow = row;
     c->g.n_glob = (double)((long long)row * col);
     c->n_local = (long long)c->g.rows * col;
@@ -563,6 +563,15 @@ int pdeode_destroy(pdeode_ctx *c) {
     if (c->ev[1]) cudaEventDestroy(c->ev[1]);
     if (c->own_stream) cudaStreamDestroy(c->own_stream);
     delete c;
+    return PDEODE_OK;
+}
+
+int pdeode_slab_rows(int row, int nranks, int rank, int *row0, int *nrows) {
+    if (row < 1 || nranks < 1 || rank < 0 || rank >= nranks) return PDEODE_ERR_ARG;
+    const int r0 = (int)((long long)rank * row / nranks);
+    const int r1 = (int)((long long)(rank + 1) * row / nranks);
+    if (row0) *row0 = r0;
+    if (nrows) *nrows = r1 - r0;
     return PDEODE_OK;
 }
 

@@ -72,6 +72,7 @@ def _lib():
         "pdeode_nccl_unique_id": [vp],
         "pdeode_destroy": [vp],
         "pdeode_local_rows": [vp, ip, ip],
+        "pdeode_slab_rows": [C.c_int, C.c_int, C.c_int, ip, ip],
         "pdeode_set_stream": [vp, vp],
         "pdeode_set_state": [vp, vp, vp],
         "pdeode_get_state": [vp, vp, vp],
