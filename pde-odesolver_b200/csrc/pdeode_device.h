@@ -120,6 +120,17 @@ struct StencilArgs {
     unsigned long long wait_phase, post_phase;
 };
 
+// Arguments of the persistent CG solve (k_cg_persist).
+struct PersistArgs {
+    StencilArgs st;        // grid, scalars, d, ac, r, q, peer block, wait_phase = INIT's phase
+    double *x;             // CG iterate (Mnew)
+    double *pbuf[2];       // direction, ping-pong; pbuf[ip] is read by the first iteration
+    int ip;
+    double *red;           // [2][2][G] partial sums of the grid-wide reductions
+    unsigned int *bar;     // {arrival count, generation} of the grid barrier
+    int nstrips, nchunks;  // G = nstrips * nchunks CTAs, one tile each
+};
+
 struct UpdateArgs {
     GridDesc g;
     DevScal *S;
@@ -176,7 +187,11 @@ cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, lon
 // Launch shape of the 5-point kernels for one context.
 struct LaunchCfg {
     int BS, TR, DEPTH, variant;
+    // persistent CG solve: 0 = off, else one cooperative launch per solve with
+    // p_nstrips * p_nchunks CTAs of p_BS consumer threads
+    int persist, p_BS, p_nstrips, p_nchunks;
 };
+cudaError_t launch_cg_persist(const PersistArgs &a, int BS, cudaStream_t st);
 // Heuristic defaults for a grid, then PDEODE_BS / PDEODE_TR / PDEODE_DEPTH /
 // PDEODE_VARIANT (reg|bulk) overrides from the environment.
 LaunchCfg launch_config(const GridDesc &g);

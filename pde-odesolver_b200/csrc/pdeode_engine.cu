@@ -52,6 +52,8 @@ struct pdeode_ctx {
     bool warm = false;            // false until the first solve: x0 = 0 (D8)
 
     DevScal *S = nullptr;
+    double *red = nullptr;            // persistent solve: grid-wide reduction buffers
+    unsigned int *bar = nullptr;      // persistent solve: grid barrier
     double *partials = nullptr;
     int max_blocks = 0;
     double *trace = nullptr;
@@ -234,9 +236,36 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         if (rc) return rc;
     }
 
+    const int ip0 = c->ip;
+    if (c->cfg.persist && sums_mode(c) != SUMS_RAW) {
+        // the whole CG loop in one cooperative launch (k_cg_persist)
+        PersistArgs pa{};
+        pa.st = stencil_args(c);
+        pa.st.wait_phase = c->phase;             // posted by the INIT just launched
+        pa.x = x;
+        pa.pbuf[0] = c->pbuf[0]; pa.pbuf[1] = c->pbuf[1]; pa.ip = c->ip;
+        pa.red = c->red; pa.bar = c->bar;
+        pa.nstrips = c->cfg.p_nstrips; pa.nchunks = c->cfg.p_nchunks;
+        CK(launch_cg_persist(pa, c->cfg.p_BS, c->stream));
+        c->launches++;
+        int rc = snapshot(c, 0);
+        if (rc) return rc;
+        if ((rc = wait_snapshot(c, 0))) return rc;
+        const DevScal &fin = c->snap[0].s;
+        if (fin.error) {
+            c->err = "peer exchange timed out (a rank stopped posting)";
+            return PDEODE_ERR_CUDA;
+        }
+        c->phase += 2ULL * (unsigned long long)fin.nit;   // two exchanges per iteration
+        c->ip = ip0 ^ (int)(fin.nit & 1);
+        c->p = c->pbuf[c->ip];
+        *nit_out = fin.nit;
+        *stop_out = fin.stop;
+        return PDEODE_OK;
+    }
+
     // CG iterations in chunks; the device flags convergence, later launches
     // of a finished solve return at once.
-    const int ip0 = c->ip;
     const int pred = std::max(1, c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)]);
     long long launched = 0;
     int slot = 0;
@@ -476,6 +505,12 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     // the marching kernels never launch more CTAs than stencil_max_blocks(g, TR)
     c->max_blocks = std::max(stencil_max_blocks(c->g, c->cfg.TR), std::max(stream_blocks(), 512));
     CK(cudaMalloc(&c->partials, sizeof(double) * 8 * (size_t)c->max_blocks));
+    {
+        const size_t G = (size_t)std::max(1, c->cfg.p_nstrips * c->cfg.p_nchunks);
+        CK(cudaMalloc(&c->red, sizeof(double) * 4 * G));
+        CK(cudaMalloc(&c->bar, 2 * sizeof(unsigned int)));
+        CK(cudaMemset(c->bar, 0, 2 * sizeof(unsigned int)));
+    }
     CK(cudaMalloc(&c->S, sizeof(DevScal)));
     CK(cudaMemset(c->S, 0, sizeof(DevScal)));
     CK(cudaMallocHost(&c->snap, 2 * sizeof(Snapshot)));
@@ -555,6 +590,8 @@ int pdeode_destroy(pdeode_ctx *c) {
     if (c->comm) nccl().CommDestroy(c->comm);
     for (int k = 0; k < pdeode_ctx::NARR; ++k) if (c->base[k]) cudaFree(c->base[k]);
     if (c->partials) cudaFree(c->partials);
+    if (c->red) cudaFree(c->red);
+    if (c->bar) cudaFree(c->bar);
     if (c->S) cudaFree(c->S);
     if (c->trace) cudaFree(c->trace);
     if (c->gather) cudaFree(c->gather);

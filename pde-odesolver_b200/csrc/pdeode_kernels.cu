@@ -524,17 +524,170 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
 // occupancy).  Row segments carry a 2-double halo on both sides so the west /
 // east neighbours of the strip's edge columns come from the same copy.
 template <int BS, int DEPTH>
+struct Ring {
+    static constexpr int TC = 2 * BS;          // columns per strip
+    static constexpr int SEG = TC + 4;         // doubles per staged row segment (halo 2 + 2)
+    static constexpr size_t BYTES = (size_t)DEPTH * (3 * SEG + TC) * sizeof(double) + 2 * DEPTH * 8;
+    double *s_r, *s_p, *s_d, *s_ac;
+    unsigned long long *full, *empty;
+    __device__ __forceinline__ void carve(unsigned char *raw) {
+        s_r = reinterpret_cast<double *>(raw);                     // [DEPTH][SEG]
+        s_p = s_r + DEPTH * SEG;                                   // [DEPTH][SEG]
+        s_d = s_p + DEPTH * SEG;                                   // [DEPTH][SEG]
+        s_ac = s_d + DEPTH * SEG;                                  // [DEPTH][TC]
+        full = reinterpret_cast<unsigned long long *>(s_ac + DEPTH * TC);
+        empty = full + DEPTH;
+    }
+    __device__ __forceinline__ void init_barriers() {
+        for (int s = 0; s < DEPTH; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BS / 32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+};
+
+// Producer lane: rows i_begin-1 .. i_end of one strip into the ring.  K counts
+// the rows this CTA has ever pushed through the ring (slot = K % DEPTH, use
+// number = K / DEPTH gives the mbarrier parity), so tiles and CG iterations
+// can follow one another without re-initialising the barriers.
+template <int BS, int DEPTH>
+__device__ __forceinline__ void bulk_produce(const Ring<BS, DEPTH> &R, const GridDesc &g,
+                                             const double *r, const double *p_in,
+                                             const double *d, const double *ac, bool firstit,
+                                             int jt, int i_begin, int i_end, long long K) {
+    constexpr int TC = Ring<BS, DEPTH>::TC, SEG = Ring<BS, DEPTH>::SEG;
+    const int nstage = (i_end - i_begin) + 2;
+    // segment [jt-2, jt-2+seglen): never past 2 doubles beyond the row (guard)
+    const unsigned segbytes = (unsigned)min(SEG, g.P + 4 - jt) * 8u;
+    const unsigned acbytes = (unsigned)min(TC, g.P - jt) * 8u;
+    for (int k = 0; k < nstage; ++k, ++K) {
+        const int s = (int)(K % DEPTH);
+        if (K >= DEPTH) mbar_wait(&R.empty[s], (unsigned)((K / DEPTH) - 1) & 1u);
+        const int i = i_begin - 1 + k;
+        const long long off = (long long)i * g.P + (jt - 2);
+        const bool has_ac = (k >= 1 && k <= nstage - 2);
+        const unsigned tx = segbytes * (firstit ? 2u : 3u) + (has_ac ? acbytes : 0u);
+        mbar_expect_tx(&R.full[s], tx);
+        bulk_g2s(R.s_r + s * SEG, r + off, segbytes, &R.full[s]);
+        if (!firstit) bulk_g2s(R.s_p + s * SEG, p_in + off, segbytes, &R.full[s]);
+        bulk_g2s(R.s_d + s * SEG, d + off, segbytes, &R.full[s]);
+        if (has_ac) bulk_g2s(R.s_ac + s * TC, ac + off + 2, acbytes, &R.full[s]);
+    }
+}
+
+// Consumers: p = r + beta p ; q = A p on rows [i_begin, i_end) of one strip;
+// adds p.q and p.p of those rows to acc0 / acc1.
+template <int BS, int DEPTH>
+__device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const GridDesc &g,
+                                             double h, double *p_out, double *q_out,
+                                             bool firstit, double beta, int jt, int i_begin,
+                                             int i_end, long long K, bool ghost_top,
+                                             bool ghost_bot, double &acc0, double &acc1) {
+    constexpr int TC = Ring<BS, DEPTH>::TC, SEG = Ring<BS, DEPTH>::SEG;
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int j0 = jt + 2 * tid;
+    const bool inrow = j0 < g.P;
+    const bool firstc0 = (j0 == 0);
+    const bool lastc0 = (j0 == g.col - 1), lastc1 = (j0 + 1 == g.col - 1);
+    const bool valid0 = j0 < g.col, valid1 = j0 + 1 < g.col;
+    const int c0 = 2 * tid + 2;                  // my pair inside a staged segment
+    const int ce = (lane == 0) ? c0 - 1 : c0 + 2;  // edge lanes: west / east halo cell
+
+    double2 vN, vC, vS, dN, dC, dS, acC, acS;
+    double veC = 0.0, deC = 0.0, veS = 0.0, deS = 0.0;   // edge-lane neighbours
+    vN = vC = vS = dN = dC = dS = acC = acS = make_double2(0.0, 0.0);
+
+    // fetch one staged row into (v, d, ac, ve, de)
+    auto take = [&](long long kk, double2 &v, double2 &d, double2 &ac, double &ve, double &de) {
+        const int s = (int)(kk % DEPTH);
+        mbar_wait(&R.full[s], (unsigned)(kk / DEPTH) & 1u);
+        const double *sr = R.s_r + s * SEG, *sp = R.s_p + s * SEG, *sd = R.s_d + s * SEG;
+        if (inrow) {
+            const double2 r2 = *reinterpret_cast<const double2 *>(sr + c0);
+            d = *reinterpret_cast<const double2 *>(sd + c0);
+            ac = *reinterpret_cast<const double2 *>(R.s_ac + s * TC + 2 * tid);
+            if (firstit) {
+                v = r2;                                            // CG:64
+            } else {
+                const double2 p2 = *reinterpret_cast<const double2 *>(sp + c0);
+                v.x = r2.x + beta * p2.x;                          // CG:71
+                v.y = r2.y + beta * p2.y;
+            }
+            if (lane == 0 || lane == 31) {
+                ve = firstit ? sr[ce] : sr[ce] + beta * sp[ce];
+                de = sd[ce];
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&R.empty[s]);
+    };
+
+    double2 dummy;
+    double dum1, dum2;
+    take(K, vN, dN, dummy, dum1, dum2);
+    take(K + 1, vC, dC, acC, veC, deC);
+    long long off = (long long)i_begin * g.P + j0;
+    if (ghost_top && i_begin == 0 && inrow) st2(p_out + off - g.P, vN);
+
+    for (int i = i_begin; i < i_end; ++i, off += g.P) {
+        take(K + (i - i_begin) + 2, vS, dS, acS, veS, deS);
+        double vW0 = __shfl_up_sync(FULL, vC.y, 1);
+        double dW0 = __shfl_up_sync(FULL, dC.y, 1);
+        double vE1 = __shfl_down_sync(FULL, vC.x, 1);
+        double dE1 = __shfl_down_sync(FULL, dC.x, 1);
+        if (lane == 0) { vW0 = veC; dW0 = deC; }
+        if (lane == 31) { vE1 = veC; dE1 = deC; }
+        if (inrow) {
+            const int gi = g.row0 + i;
+            const bool first = (gi == 0);
+            const bool lastrow = (gi == g.grow - 1);
+            const bool quirkrow = (gi == g.grow - 2);
+            const double aN0 = h * (dN.x + dC.x), aN1 = h * (dN.y + dC.y);
+            const double aS0 = h * (dS.x + dC.x), aS1 = h * (dS.y + dC.y);
+            const double aW0 = h * (dW0 + dC.x);
+            const double aM = h * (dC.y + dC.x);
+            const double aE1 = h * (dE1 + dC.y);
+            double2 q2;
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const bool firstc = c ? false : firstc0;
+                const bool lastc = c ? lastc1 : lastc0;
+                const bool lastq = lastrow || (quirkrow && lastc);
+                const double aN = c ? aN1 : aN0, aS = c ? aS1 : aS0;
+                const double aW = c ? aM : aW0, aE = c ? aE1 : aM;
+                const double xN = c ? vN.y : vN.x, xS = c ? vS.y : vS.x;
+                const double xC = c ? vC.y : vC.x;
+                const double xW = c ? vC.x : vW0, xE = c ? vE1 : vC.y;
+                const double A1 = first ? 0.0 : (lastq ? -(aN + aN) : -aN);
+                const double A5 = lastq ? 0.0 : (first ? -(aS + aS) : -aS);
+                const double A2 = firstc ? 0.0 : (lastc ? -(aW + aW) : -aW);
+                const double A4 = lastc ? 0.0 : (firstc ? -(aE + aE) : -aE);
+                const double A3 = c ? acC.y : acC.x;
+                double y = A1 * xN;
+                y = y + A2 * xW;
+                y = y + A3 * xC;
+                y = y + A4 * xE;
+                y = y + A5 * xS;
+                const bool valid = c ? valid1 : valid0;
+                const double qq = valid ? y : 0.0;
+                if (c) q2.y = qq; else q2.x = qq;
+                acc0 += xC * qq;
+                acc1 += valid ? xC * xC : 0.0;
+            }
+            st2(p_out + off, vC);
+            st2(q_out + off, q2);
+        }
+        vN = vC; vC = vS; dN = dC; dC = dS; acC = acS; veC = veS; deC = deS;
+    }
+    if (ghost_bot && i_end == g.rows && inrow) st2(p_out + off, vC);
+}
+
+template <int BS, int DEPTH>
 __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
-    constexpr int TC = 2 * BS;          // columns per strip
-    constexpr int SEG = TC + 4;         // doubles per staged row segment (halo 2 + 2)
+    constexpr int TC = Ring<BS, DEPTH>::TC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    double *s_r = reinterpret_cast<double *>(smem_raw);            // [DEPTH][SEG]
-    double *s_p = s_r + DEPTH * SEG;                               // [DEPTH][SEG]
-    double *s_d = s_p + DEPTH * SEG;                               // [DEPTH][SEG]
-    double *s_ac = s_d + DEPTH * SEG;                              // [DEPTH][TC]
-    unsigned long long *full = reinterpret_cast<unsigned long long *>(s_ac + DEPTH * TC);
-    unsigned long long *empty = full + DEPTH;
     __shared__ double sm[64];
+    Ring<BS, DEPTH> R;
+    R.carve(smem_raw);
 
     DevScal *S = a.S;
     if (S->done) return;
@@ -553,137 +706,17 @@ __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
     const int jt = blockIdx.x * TC;                 // first column of the strip
     const int i_begin = blockIdx.y * a.TR;
     const int i_end = min(i_begin + a.TR, g.rows);
-    const int nstage = (i_end - i_begin) + 2;       // rows i_begin-1 .. i_end
-    // segment [jt-2, jt-2+seglen): never past 2 doubles beyond the row (guard)
-    const int seglen = min(SEG, g.P + 4 - jt);
-    const unsigned segbytes = (unsigned)seglen * 8u;
-    const int aclen = min(TC, g.P - jt);
-    const unsigned acbytes = (unsigned)aclen * 8u;
 
-    if (tid == 0) {
-        for (int s = 0; s < DEPTH; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], BS / 32); }
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
+    if (tid == 0) R.init_barriers();
     __syncthreads();
 
     double acc0 = 0.0, acc1 = 0.0;
-
     if (tid >= BS) {
-        // ---------------- producer warp: one lane issues the copies
-        if (tid == BS) {
-            for (int k = 0; k < nstage; ++k) {
-                const int s = k % DEPTH;
-                if (k >= DEPTH) mbar_wait(&empty[s], ((k / DEPTH) - 1) & 1);
-                const int i = i_begin - 1 + k;
-                const long long off = (long long)i * g.P + (jt - 2);
-                const bool has_ac = (k >= 1 && k <= nstage - 2);
-                const unsigned tx = segbytes * (firstit ? 2u : 3u) + (has_ac ? acbytes : 0u);
-                mbar_expect_tx(&full[s], tx);
-                bulk_g2s(s_r + s * SEG, a.r + off, segbytes, &full[s]);
-                if (!firstit) bulk_g2s(s_p + s * SEG, a.p_in + off, segbytes, &full[s]);
-                bulk_g2s(s_d + s * SEG, a.d + off, segbytes, &full[s]);
-                if (has_ac) bulk_g2s(s_ac + s * TC, a.ac + off + 2, acbytes, &full[s]);
-            }
-        }
+        if (tid == BS)
+            bulk_produce<BS, DEPTH>(R, g, a.r, a.p_in, a.d, a.ac, firstit, jt, i_begin, i_end, 0);
     } else {
-        // ---------------- consumers
-        const int lane = tid & 31;
-        const int j0 = jt + 2 * tid;
-        const bool inrow = j0 < g.P;
-        const double h = a.np.h;
-        const bool firstc0 = (j0 == 0);
-        const bool lastc0 = (j0 == g.col - 1), lastc1 = (j0 + 1 == g.col - 1);
-        const bool valid0 = j0 < g.col, valid1 = j0 + 1 < g.col;
-        const int c0 = 2 * tid + 2;                  // my pair inside a staged segment
-        const int ce = (lane == 0) ? c0 - 1 : c0 + 2;  // edge lanes: west / east halo cell
-
-        double2 vN, vC, vS, dN, dC, dS, acC, acS;
-        double veC = 0.0, deC = 0.0, veS = 0.0, deS = 0.0;   // edge-lane neighbours
-        vN = vC = vS = dN = dC = dS = acC = acS = make_double2(0.0, 0.0);
-
-        // fetch one staged row into (v, d, ac, ve, de)
-        auto take = [&](int k, double2 &v, double2 &d, double2 &ac, double &ve, double &de) {
-            const int s = k % DEPTH;
-            mbar_wait(&full[s], (k / DEPTH) & 1);
-            const double *sr = s_r + s * SEG, *sp = s_p + s * SEG, *sd = s_d + s * SEG;
-            if (inrow) {
-                const double2 r2 = *reinterpret_cast<const double2 *>(sr + c0);
-                d = *reinterpret_cast<const double2 *>(sd + c0);
-                ac = *reinterpret_cast<const double2 *>(s_ac + s * TC + 2 * tid);
-                if (firstit) {
-                    v = r2;                                            // CG:64
-                } else {
-                    const double2 p2 = *reinterpret_cast<const double2 *>(sp + c0);
-                    v.x = r2.x + beta * p2.x;                          // CG:71
-                    v.y = r2.y + beta * p2.y;
-                }
-                if (lane == 0 || lane == 31) {
-                    ve = firstit ? sr[ce] : sr[ce] + beta * sp[ce];
-                    de = sd[ce];
-                }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[s]);
-        };
-
-        double2 dummy;
-        double dum1, dum2;
-        take(0, vN, dN, dummy, dum1, dum2);
-        take(1, vC, dC, acC, veC, deC);
-        long long off = (long long)i_begin * g.P + j0;
-        if (a.write_ghost_top && i_begin == 0 && inrow) st2(a.p + off - g.P, vN);
-
-        for (int i = i_begin; i < i_end; ++i, off += g.P) {
-            take(i - i_begin + 2, vS, dS, acS, veS, deS);
-            double vW0 = __shfl_up_sync(FULL, vC.y, 1);
-            double dW0 = __shfl_up_sync(FULL, dC.y, 1);
-            double vE1 = __shfl_down_sync(FULL, vC.x, 1);
-            double dE1 = __shfl_down_sync(FULL, dC.x, 1);
-            if (lane == 0) { vW0 = veC; dW0 = deC; }
-            if (lane == 31) { vE1 = veC; dE1 = deC; }
-            if (inrow) {
-                const int gi = g.row0 + i;
-                const bool first = (gi == 0);
-                const bool lastrow = (gi == g.grow - 1);
-                const bool quirkrow = (gi == g.grow - 2);
-                const double aN0 = h * (dN.x + dC.x), aN1 = h * (dN.y + dC.y);
-                const double aS0 = h * (dS.x + dC.x), aS1 = h * (dS.y + dC.y);
-                const double aW0 = h * (dW0 + dC.x);
-                const double aM = h * (dC.y + dC.x);
-                const double aE1 = h * (dE1 + dC.y);
-                double2 q2;
-#pragma unroll
-                for (int c = 0; c < 2; ++c) {
-                    const bool firstc = c ? false : firstc0;
-                    const bool lastc = c ? lastc1 : lastc0;
-                    const bool lastq = lastrow || (quirkrow && lastc);
-                    const double aN = c ? aN1 : aN0, aS = c ? aS1 : aS0;
-                    const double aW = c ? aM : aW0, aE = c ? aE1 : aM;
-                    const double xN = c ? vN.y : vN.x, xS = c ? vS.y : vS.x;
-                    const double xC = c ? vC.y : vC.x;
-                    const double xW = c ? vC.x : vW0, xE = c ? vE1 : vC.y;
-                    const double A1 = first ? 0.0 : (lastq ? -(aN + aN) : -aN);
-                    const double A5 = lastq ? 0.0 : (first ? -(aS + aS) : -aS);
-                    const double A2 = firstc ? 0.0 : (lastc ? -(aW + aW) : -aW);
-                    const double A4 = lastc ? 0.0 : (firstc ? -(aE + aE) : -aE);
-                    const double A3 = c ? acC.y : acC.x;
-                    double y = A1 * xN;
-                    y = y + A2 * xW;
-                    y = y + A3 * xC;
-                    y = y + A4 * xE;
-                    y = y + A5 * xS;
-                    const bool valid = c ? valid1 : valid0;
-                    const double qq = valid ? y : 0.0;
-                    if (c) q2.y = qq; else q2.x = qq;
-                    acc0 += xC * qq;
-                    acc1 += valid ? xC * xC : 0.0;
-                }
-                st2(a.p + off, vC);
-                st2(a.q + off, q2);
-            }
-            vN = vC; vC = vS; dN = dC; dC = dS; acC = acS; veC = veS; deC = deS;
-        }
-        if (a.write_ghost_bot && i_end == g.rows && inrow) st2(a.p + off, vC);
+        bulk_consume<BS, DEPTH>(R, g, a.np.h, a.p, a.q, firstit, beta, jt, i_begin, i_end, 0,
+                                a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1);
     }
 
     const int nb = gridDim.x * gridDim.y;
@@ -766,6 +799,177 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         } else {
             S->part[0] = rr; S->part[1] = xx;
         }
+    }
+}
+
+// ---------------------------------------------------------------- persistent CG solve
+
+// Grid-wide barrier for a cooperative launch (all CTAs resident): one arrival
+// counter and a generation word in global memory.  The generation is read
+// before arriving, so a CTA that races ahead into the next barrier cannot be
+// mistaken for a late arrival of this one.
+__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int G, bool sys) {
+    if (sys) __threadfence_system();    // peer mode: ghost rows stored into other GPUs
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        volatile unsigned int *gen = bar + 1;
+        const unsigned int g0 = *gen;
+        __threadfence();
+        if (atomicAdd(bar, 1u) == G - 1) {
+            bar[0] = 0u;
+            __threadfence();
+            atomicAdd(bar + 1, 1u);
+        } else {
+            while (*gen == g0) { }
+        }
+        __threadfence();
+    }
+    __syncthreads();
+}
+
+// Grid-wide sum of a pair: every CTA stores its partial, all meet at the
+// barrier, then every CTA adds all partials in the same fixed order -- every
+// CTA (and, in peer mode, every rank) ends up with the same bits, so each can
+// take the stop decision on its own.  red: [2][G] doubles.
+__device__ __forceinline__ void grid_allsum2(double &a, double &b, double *red, unsigned int *bar,
+                                             int G, double *sm, double *s_tot, bool sys) {
+    block_sum2(a, b, sm);
+    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; }
+    grid_barrier(bar, (unsigned int)G, sys);
+    double x = 0.0, y = 0.0;
+    for (int i = threadIdx.x; i < G; i += blockDim.x) {
+        x += __ldcg(red + i);
+        y += __ldcg(red + G + i);
+    }
+    block_sum2(x, y, sm);
+    if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; }
+    __syncthreads();
+    a = s_tot[0]; b = s_tot[1];
+    __syncthreads();
+}
+
+// The whole CG solve (CG:54-94) in one cooperative launch: every CTA owns one
+// tile (a 2*BS-column strip x a row range) for the entire solve and alternates
+//   A: p = r + beta p ; q = A p ; p.q ; p.p      (bulk-async staged, as k_spmv_bulk)
+//   B: x += alfa p ; r -= alfa q ; r.r ; x.x     (its own cells only)
+// with one grid-wide sum after each.  All CTAs hold the same scalars and take
+// the same stop decision (CG:87-90), so no kernel boundary, host round trip
+// or scalar broadcast is needed per iteration; in peer mode CTA 0 also trades
+// the sums with the other GPUs and boundary rows of r go straight into the
+// neighbours' ghost rows.  Used where launch latency would dominate (small
+// grids, thin slabs of a multi-GPU run); results are bit-identical to the
+// kernel-per-phase path only up to the order of the partial sums.
+template <int BS, int DEPTH>
+__global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
+    constexpr int TC = Ring<BS, DEPTH>::TC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double sm[64];
+    __shared__ double s_tot[2];
+    Ring<BS, DEPTH> R;
+    R.carve(smem_raw);
+
+    const StencilArgs &a = A.st;
+    DevScal *S = a.S;
+    const GridDesc g = a.g;
+    const int G = gridDim.x;
+    const int tid = threadIdx.x;
+    const bool peer = (a.fuse_scalars == SUMS_PEER);
+    const int strip = blockIdx.x % A.nstrips, chunk = blockIdx.x / A.nstrips;
+    const int jt = strip * TC;
+    const int i_begin = (int)((long long)chunk * g.rows / A.nchunks);
+    const int i_end = (int)((long long)(chunk + 1) * g.rows / A.nchunks);
+    const int j0 = jt + 2 * tid;
+    const bool worker = (tid < BS) && (j0 < g.P);
+
+    if (tid == 0) R.init_barriers();
+    __syncthreads();
+
+    unsigned long long ph = a.wait_phase;
+    double rho, xx, rho_old = 0.0;
+    if (peer) {
+        peer_wait_sums(a.pc, ph, S, rho, xx);          // posted by the INIT kernel
+    } else {
+        rho = S->rho; xx = S->xx;
+    }
+    const long long maxit = S->maxit;
+    const double n_glob = g.n_glob, tol2 = a.np.tol2;
+    // peer mode: rows 0 and rows-1 of r are also the neighbours' ghost rows
+    double *const up = peer && a.pc.r_up ? a.pc.r_up + (long long)a.pc.rows_up * g.P : nullptr;
+    double *const dn = peer && a.pc.r_dn ? a.pc.r_dn - g.P : nullptr;
+
+    long long K = 0, it = 0;
+    int ip = A.ip, stop = 0, sel = 0;
+    double alfa = 0.0, err2 = 0.0, normx = 0.0, pq = 0.0, pp = 0.0;
+    for (;;) {
+        ++it;                                                        // CG:55
+        const bool firstit = (it == 1);
+        const double beta = firstit ? 0.0 : rho / rho_old;           // CG:68
+        const double *p_in = A.pbuf[ip];
+        double *p_out = A.pbuf[ip ^ 1];
+        // ---- phase A
+        double acc0 = 0.0, acc1 = 0.0;
+        if (tid >= BS) {
+            if (tid == BS) {
+                asm volatile("fence.proxy.async;" ::: "memory");     // r, p were written by plain stores
+                bulk_produce<BS, DEPTH>(R, g, a.r, p_in, a.d, a.ac, firstit, jt, i_begin, i_end, K);
+            }
+        } else {
+            bulk_consume<BS, DEPTH>(R, g, a.np.h, p_out, a.q, firstit, beta, jt, i_begin, i_end, K,
+                                    a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1);
+        }
+        K += (i_end - i_begin) + 2;
+        grid_allsum2(acc0, acc1, A.red + (size_t)sel * 2 * G, A.bar, G, sm, s_tot, false);
+        sel ^= 1;
+        if (peer) {
+            ++ph;
+            if (blockIdx.x == 0 && tid == 0) peer_post(a.pc, ph, acc0, acc1);
+            peer_wait_sums(a.pc, ph, S, acc0, acc1);
+        }
+        pq = acc0; pp = acc1;
+        alfa = rho / pq;                                             // CG:77
+        err2 = fabs(alfa) * sqrt(pp) / n_glob;                       // CG:87
+        normx = sqrt(xx) / n_glob;                                   // CG:57
+        stop = 0;
+        if (it > maxit) stop = -1;                                   // CG:88
+        if (err2 < tol2 * normx) stop = stop - 100;                  // CG:90
+        if (blockIdx.x == 0 && tid == 0 && a.trace && it <= (long long)S->trace_cap) {
+            double *t = a.trace + 5 * (it - 1);
+            t[0] = rho; t[1] = pq; t[2] = alfa; t[3] = err2; t[4] = normx;
+        }
+        // ---- phase B: my own cells (the ones whose p and q I just wrote)
+        double rr = 0.0, xn = 0.0;
+        if (worker) {
+            long long off = (long long)i_begin * g.P + j0;
+            for (int i = i_begin; i < i_end; ++i, off += g.P) {
+                double2 x2 = ld2(A.x + off), p2 = ld2(p_out + off);
+                double2 r2 = ld2(a.r + off), q2 = ld2(a.q + off);
+                x2.x = x2.x + alfa * p2.x; x2.y = x2.y + alfa * p2.y;  // CG:80
+                r2.x = r2.x - alfa * q2.x; r2.y = r2.y - alfa * q2.y;  // CG:81
+                st2(A.x + off, x2);
+                st2(a.r + off, r2);
+                if (up && i == 0) st2(up + j0, r2);
+                if (dn && i == g.rows - 1) st2(dn + j0, r2);
+                rr += r2.x * r2.x; rr += r2.y * r2.y;
+                xn += x2.x * x2.x; xn += x2.y * x2.y;
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");         // next phase A reads r via bulk copies
+        }
+        grid_allsum2(rr, xn, A.red + (size_t)sel * 2 * G, A.bar, G, sm, s_tot, peer);
+        sel ^= 1;
+        if (peer) {
+            ++ph;
+            if (blockIdx.x == 0 && tid == 0) peer_post(a.pc, ph, rr, xn);
+            peer_wait_sums(a.pc, ph, S, rr, xn);
+        }
+        rho_old = rho; rho = rr; xx = xn;                            // CG:56,59,57
+        ip ^= 1;
+        if (stop != 0) break;
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        S->nit = it; S->stop = stop; S->done = 1; S->finished = 1;
+        S->rho = rho; S->rho_old = rho_old; S->xx = xx;
+        S->alfa = alfa; S->err2 = err2; S->normx = normx; S->pq = pq; S->pp = pp;
+        if (a.trace) S->trace_len = (int)min(it, (long long)S->trace_cap);
     }
 }
 
@@ -893,6 +1097,45 @@ __global__ void __launch_bounds__(256) k_mass(const MassArgs a) {
 
 static inline int cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 
+constexpr int PERSIST_DEPTH = 4;
+
+template <int BS>
+static int persist_occupancy() {
+    constexpr size_t smem = Ring<BS, PERSIST_DEPTH>::BYTES;
+    if (cudaFuncSetAttribute(k_cg_persist<BS, PERSIST_DEPTH>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cg_persist<BS, PERSIST_DEPTH>, BS + 32,
+                                                      smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    return n;
+}
+
+static int persist_ctas_per_sm(int bs) {
+    if (bs == 64) return persist_occupancy<64>();
+    if (bs == 128) return persist_occupancy<128>();
+    return persist_occupancy<256>();
+}
+
+template <int BS>
+static cudaError_t launch_cg_persist_t(const PersistArgs &a, cudaStream_t st) {
+    void *args[] = {const_cast<PersistArgs *>(&a)};
+    return cudaLaunchCooperativeKernel((const void *)k_cg_persist<BS, PERSIST_DEPTH>,
+                                       dim3(a.nstrips * a.nchunks), dim3(BS + 32), args,
+                                       Ring<BS, PERSIST_DEPTH>::BYTES, st);
+}
+
+cudaError_t launch_cg_persist(const PersistArgs &a, int BS, cudaStream_t st) {
+    if (BS == 64) return launch_cg_persist_t<64>(a, st);
+    if (BS == 128) return launch_cg_persist_t<128>(a, st);
+    return launch_cg_persist_t<256>(a, st);
+}
+
 LaunchCfg launch_config(const GridDesc &g) {
     if (const char *e = getenv("PDEODE_STREAM_CTAS")) {
         const int v = atoi(e);
@@ -929,6 +1172,24 @@ LaunchCfg launch_config(const GridDesc &g) {
         const int v = atoi(e);
         if (v >= 2 && v <= 8) c.DEPTH = v;
     }
+
+    // Persistent solve: one tile per CTA, all CTAs resident (cooperative launch).
+    // Narrower strips for narrower grids so that enough CTAs exist.
+    c.p_BS = (g.P <= 1024) ? 64 : (g.P <= 2048 ? 128 : 256);
+    if (const char *e = getenv("PDEODE_PERSIST_BS")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) c.p_BS = v;
+    }
+    const int per_sm = persist_ctas_per_sm(c.p_BS);
+    c.p_nstrips = cdiv(g.P, 2 * c.p_BS);
+    int nch = per_sm * g_num_sms / c.p_nstrips;
+    const int by_rows = g.rows / 4 > 0 ? g.rows / 4 : 1;
+    if (nch > by_rows) nch = by_rows;
+    c.p_nchunks = nch;
+    // default: where a CG iteration is short enough for launch latency to matter
+    const long long cells = (long long)g.rows * g.P;
+    c.persist = (nch >= 1 && c.variant == 1 && cells <= (4LL << 20)) ? 1 : 0;
+    if (const char *e = getenv("PDEODE_PERSIST")) c.persist = (atoi(e) != 0 && nch >= 1) ? 1 : 0;
     return c;
 }
 
@@ -966,8 +1227,8 @@ cudaError_t launch_stencil_init(const StencilArgs &a, cudaStream_t st) {
 }
 template <int BS, int DEPTH>
 static cudaError_t launch_spmv_bulk(const StencilArgs &a, cudaStream_t st) {
-    constexpr int TC = 2 * BS, SEG = TC + 4;
-    constexpr size_t smem = (size_t)DEPTH * (3 * SEG + TC) * sizeof(double) + 2 * DEPTH * 8;
+    constexpr int TC = 2 * BS;
+    constexpr size_t smem = Ring<BS, DEPTH>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
         cudaError_t e = cudaFuncSetAttribute(k_spmv_bulk<BS, DEPTH>,
