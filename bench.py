@@ -174,7 +174,7 @@ def run_reference(args):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(out), flush=True)
+    emit(out)
 
 
 def workload_config(args, nranks):
@@ -189,7 +189,26 @@ def workload_config(args, nranks):
     }
 
 
+_REAL_STDOUT = None
+
+
+def quiet_stdout():
+    """Everything but the final JSON line goes to stderr: NCCL prints a version
+    banner on stdout, and the contract is ONE JSON line."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
+
+
+def emit(obj):
+    sys.stdout.flush()
+    line = (json.dumps(obj) + "\n").encode()
+    os.write(_REAL_STDOUT if _REAL_STDOUT is not None else 1, line)
+
+
 def main():
+    quiet_stdout()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
@@ -367,7 +386,7 @@ def main():
             "cg_iterations": it_res, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
         }
-        print(json.dumps(out), flush=True)
+        emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

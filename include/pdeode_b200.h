@@ -78,6 +78,9 @@ int pdeode_nccl_unique_id(void *id_out);
 
 int pdeode_destroy(pdeode_ctx *ctx);
 
+/* Number of CUDA devices this process can use (0 and PDEODE_ERR_NODEVICE if none). */
+int pdeode_device_count(int *count);
+
 /* The row-slab partition itself (no device needed): rank's rows of a `row`-row
  * grid split over nranks. */
 int pdeode_slab_rows(int row, int nranks, int rank, int *row0, int *nrows);

@@ -603,6 +603,18 @@ int pdeode_destroy(pdeode_ctx *c) {
     return PDEODE_OK;
 }
 
+int pdeode_device_count(int *count) {
+    if (!count) return PDEODE_ERR_ARG;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0) {
+        cudaGetLastError();
+        *count = 0;
+        return PDEODE_ERR_NODEVICE;
+    }
+    *count = n;
+    return PDEODE_OK;
+}
+
 int pdeode_slab_rows(int row, int nranks, int rank, int *row0, int *nrows) {
     if (row < 1 || nranks < 1 || rank < 0 || rank >= nranks) return PDEODE_ERR_ARG;
     const int r0 = (int)((long long)rank * row / nranks);

@@ -210,6 +210,9 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
 __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
     double v;
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
@@ -258,9 +261,9 @@ __device__ __forceinline__ void peer_post(const PeerComm &pc, unsigned long long
         double *v = pc.peer_slots[r] + ((size_t)slot * PEER_MAX_RANKS + pc.rank) * 2;
         v[0] = a; v[1] = b;
     }
-    __threadfence_system();
+    __threadfence_system();     // one fence, then plain flag stores: a release per flag would fence each
     for (int r = 0; r < pc.nranks; ++r)
-        st_release_sys(pc.peer_flags[r] + slot * PEER_MAX_RANKS + pc.rank, phase);
+        st_relaxed_sys(pc.peer_flags[r] + slot * PEER_MAX_RANKS + pc.rank, phase);
 }
 
 // ---------------------------------------------------------------- D(M)
@@ -940,21 +943,32 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
         double rr = 0.0, xn = 0.0;
         if (worker) {
             long long off = (long long)i_begin * g.P + j0;
-            for (int i = i_begin; i < i_end; ++i, off += g.P) {
-                double2 x2 = ld2(A.x + off), p2 = ld2(p_out + off);
-                double2 r2 = ld2(a.r + off), q2 = ld2(a.q + off);
+            auto upd = [&](int i, long long o, double2 x2, double2 p2, double2 r2, double2 q2) {
                 x2.x = x2.x + alfa * p2.x; x2.y = x2.y + alfa * p2.y;  // CG:80
                 r2.x = r2.x - alfa * q2.x; r2.y = r2.y - alfa * q2.y;  // CG:81
-                st2(A.x + off, x2);
-                st2(a.r + off, r2);
+                st2(A.x + o, x2);
+                st2(a.r + o, r2);
                 if (up && i == 0) st2(up + j0, r2);
                 if (dn && i == g.rows - 1) st2(dn + j0, r2);
                 rr += r2.x * r2.x; rr += r2.y * r2.y;
                 xn += x2.x * x2.x; xn += x2.y * x2.y;
+            };
+            int i = i_begin;
+            for (; i + 1 < i_end; i += 2, off += 2 * g.P) {          // two rows in flight
+                const long long o1 = off + g.P;
+                const double2 xa = ld2(A.x + off), pa = ld2(p_out + off);
+                const double2 ra = ld2(a.r + off), qa = ld2(a.q + off);
+                const double2 xb = ld2(A.x + o1), pb = ld2(p_out + o1);
+                const double2 rb = ld2(a.r + o1), qb = ld2(a.q + o1);
+                upd(i, off, xa, pa, ra, qa);
+                upd(i + 1, o1, xb, pb, rb, qb);
             }
+            if (i < i_end) upd(i, off, ld2(A.x + off), ld2(p_out + off), ld2(a.r + off), ld2(a.q + off));
             asm volatile("fence.proxy.async;" ::: "memory");         // next phase A reads r via bulk copies
         }
-        grid_allsum2(rr, xn, A.red + (size_t)sel * 2 * G, A.bar, G, sm, s_tot, peer);
+        // only CTAs that stored into a neighbour GPU need the system-wide fence
+        const bool wrote_peer = (up && i_begin == 0) || (dn && i_end == g.rows);
+        grid_allsum2(rr, xn, A.red + (size_t)sel * 2 * G, A.bar, G, sm, s_tot, wrote_peer);
         sel ^= 1;
         if (peer) {
             ++ph;

@@ -73,6 +73,7 @@ def _lib():
         "pdeode_destroy": [vp],
         "pdeode_local_rows": [vp, ip, ip],
         "pdeode_slab_rows": [C.c_int, C.c_int, C.c_int, ip, ip],
+        "pdeode_device_count": [ip],
         "pdeode_set_stream": [vp, vp],
         "pdeode_set_state": [vp, vp, vp],
         "pdeode_get_state": [vp, vp, vp],

@@ -69,3 +69,31 @@ def test_solver_binary_matches_oracle_driven_host(tmp_path, name, frame_file):
                 assert float(u) == pytest.approx(float(v), rel=5e-2, abs=1e-6)
             except ValueError:
                 assert u == v
+
+
+def test_ensemble_members_equal_single_runs(tmp_path):
+    """pdeode_ensemble: every member is the same run the single-run program
+    makes (replicas, no coupling), written into <name>Output/."""
+    ge.build_cuda(); ge.build_host()
+    files = []
+    base = open(os.path.join(DATA, "square3d.txt")).read()
+    for k, h in enumerate((0.9, 0.8, 0.7, 0.6, 0.5), start=1):
+        txt = base.replace("height    = 0.9", f"height    = {h}")
+        (tmp_path / f"{k}.txt").write_text(txt)
+        files.append(f"{k}.txt")
+    exe = os.path.join(ge.BINDIR, "pdeode_ensemble")
+    env = dict(os.environ, PDEODE_SEED="1", PDEODE_MEMBERS_PER_GPU="3")
+    r = subprocess.run([exe] + files, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout + r.stderr
+    solver = os.path.join(ge.BINDIR, "pdeode_solver")
+    for k, f in enumerate(files, start=1):
+        out = tmp_path / f"{k}Output"
+        assert sorted(os.listdir(out)) == ["COprod.dat", "console.txt", f, "output.dat",
+                                           "statReport.dat", "total.dat"]
+        single = tmp_path / f"single{k}"
+        single.mkdir()
+        s = subprocess.run([solver], input=str(tmp_path / f) + "\n", text=True, capture_output=True,
+                           cwd=single, env=env, timeout=300)
+        assert s.returncode == 0
+        for name in ("total.dat", "COprod.dat", "output.dat"):
+            assert open(out / name).read() == open(single / name).read(), (k, name)

@@ -29,6 +29,22 @@ def pb():
     return pdeode_b200
 
 
+@pytest.fixture
+def engine_env(monkeypatch):
+    """Selects the CG engine of contexts created afterwards (read at pdeode_create)."""
+    def select(engine):
+        for k in ("PDEODE_PERSIST", "PDEODE_VARIANT"):
+            monkeypatch.delenv(k, raising=False)
+        if engine == "kernels":
+            monkeypatch.setenv("PDEODE_PERSIST", "0")
+        elif engine == "persistent":
+            monkeypatch.setenv("PDEODE_PERSIST", "1")
+        elif engine == "register-staged":
+            monkeypatch.setenv("PDEODE_PERSIST", "0")
+            monkeypatch.setenv("PDEODE_VARIANT", "reg")
+    return select
+
+
 def rel_l2(a, b):
     nb = np.linalg.norm(b)
     return np.linalg.norm(a - b) / (nb if nb > 0 else 1.0)
@@ -54,6 +70,10 @@ def field_tolerance(p, counts_equal, envelope):
 
 
 def run_pair(pb, row, col, over, M0, C0, steps, check_every=True, cg_tol=TOL_CG):
+    if col == 4:
+        # quasi-1D runs sit on a CG plateau near the stop threshold; the reference's own
+        # two builds differ by up to 4 iterations there (see test_golden_fixtures)
+        cg_tol = max(cg_tol, 8)
     p = pb.default_params(row, **over)
     s = pb.Solver(row, col, p)
     o = ol.Oracle(row, col, ol.default_params(row, **over))
@@ -182,7 +202,11 @@ def test_first_cg_iteration_scalars(pb):
     (64, 64, dict(dSelect=1, fSelect=5, tDel=1e-2), ("blobs", 0.3, 0.3, 4, 2), 3),
     (257, 257, {}, ("blobs", 0.02, 0.0390625, 60, 7), 4),     # shipped parameter.txt values
 ])
-def test_steps_match_oracle(pb, row, col, over, ic, steps):
+@pytest.mark.parametrize("engine", ["kernels", "persistent", "register-staged"])
+def test_steps_match_oracle(pb, engine_env, row, col, over, ic, steps, engine):
+    """Both CG engines -- one kernel per phase and the persistent cooperative
+    solve -- and the register-staged SpMV variant, against the oracle."""
+    engine_env(engine)
     if ic[0] == "ic1":
         M0, C0 = ol.ic1(row, col, ic[1], ic[2])
     else:
@@ -212,7 +236,9 @@ def test_1024_grid_matches_oracle(pb):
 
 
 @pytest.mark.parametrize("name", CASES)
-def test_golden_fixtures(pb, name):
+@pytest.mark.parametrize("engine", ["kernels", "persistent"])
+def test_golden_fixtures(pb, engine_env, name, engine):
+    engine_env(engine)
     z, row, col, over = load_case(name)
     s = pb.Solver(row, col, pb.default_params(row, **over))
     s.set_state(z["M0"], z["C0"])
@@ -223,7 +249,11 @@ def test_golden_fixtures(pb, name):
         assert g["countIters"] == z["countIters"][k]
         want = [int(v) for v in z["nits"][k][:len(g["nits"])]]
         for a, b in zip(g["nits"], want):
-            assert abs(a - b) <= TOL_CG, (name, k, g["nits"], want)
+            # quasi-1D (col = 4) runs sit on a CG plateau near the stop threshold: the
+            # reference's own serial / OpenMP builds differ by up to 4 iterations there
+            # (test_reference_is_not_self_consistent_to_1e9), so +-2 cannot hold
+            cg_tol = 8 if col == 4 else TOL_CG
+            assert abs(a - b) <= cg_tol, (name, k, g["nits"], want)
         counts_equal = counts_equal and g["nits"] == want
         tol = field_tolerance(p, counts_equal, float(z["env"][k]))
         M, Cc = s.get_state()
