@@ -102,6 +102,18 @@ int pdeode_set_state(pdeode_ctx *ctx, const double *M, const double *C);
 /* D2H of this context's slab; needed at frame times only (P:685-687). */
 int pdeode_get_state(pdeode_ctx *ctx, double *M, double *C);
 
+/* Frame output without moving whole fields.  The reference writes
+ * every filter-th row and column, filter = (row-1)/256 for row > 257, else 1
+ * (P:829-832, P:893-896).  *nrows_out x *ncols_out = the points of this
+ * context's slab that a frame contains. */
+int pdeode_frame_size(const pdeode_ctx *ctx, int filter, int *nrows_out, int *ncols_out);
+/* The M and C values printToFile writes (P:834-842), nrows_out*ncols_out each,
+ * row-major, decimated on the device. */
+int pdeode_get_frame(pdeode_ctx *ctx, int filter, double *M, double *C);
+/* The per-row column means printToFile2D writes (P:898-925), nrows_out each,
+ * summed left to right like the reference. */
+int pdeode_get_frame_rowmeans(pdeode_ctx *ctx, int filter, double *meanM, double *meanC);
+
 /* ---- the path ------------------------------------------------------- */
 
 /* One implicit time step, Picard loop included (P:700-742).  Returns this

@@ -176,6 +176,10 @@ cudaError_t launch_stencil_cg(const StencilArgs &a, cudaStream_t st);
 cudaError_t launch_update(const UpdateArgs &a, cudaStream_t st);
 cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st);
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t st);
+cudaError_t launch_decimate(const GridDesc &g, const double *M, const double *C, int filter,
+                            int first_row, int nro, int nco, double *out, cudaStream_t st);
+cudaError_t launch_rowmeans(const GridDesc &g, const double *M, const double *C, int filter,
+                            int first_row, int nro, double *out, cudaStream_t st);
 // scalar steps for the multi-rank path (sums already all-reduced into S->part)
 cudaError_t launch_scal_after_init(DevScal *S, cudaStream_t st);
 cudaError_t launch_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace,

@@ -59,6 +59,8 @@ struct pdeode_ctx {
     double *trace = nullptr;
     int trace_cap = 0;
     double *gather = nullptr;     // multi-rank diagnostics
+    double *frame_buf = nullptr;  // decimated frame staging
+    size_t frame_cap = 0;
     Snapshot *snap = nullptr;     // pinned, 2 slots
     cudaEvent_t ev[2] = {nullptr, nullptr};
     cudaStream_t own_stream = nullptr, stream = nullptr;
@@ -590,6 +592,7 @@ int pdeode_destroy(pdeode_ctx *c) {
     if (c->comm) nccl().CommDestroy(c->comm);
     for (int k = 0; k < pdeode_ctx::NARR; ++k) if (c->base[k]) cudaFree(c->base[k]);
     if (c->partials) cudaFree(c->partials);
+    if (c->frame_buf) cudaFree(c->frame_buf);
     if (c->red) cudaFree(c->red);
     if (c->bar) cudaFree(c->bar);
     if (c->S) cudaFree(c->S);
@@ -659,6 +662,69 @@ int pdeode_get_state(pdeode_ctx *c, double *M, double *C) {
     int rc;
     if ((rc = download(c, M, c->Mb[c->iM]))) return rc;
     if ((rc = download(c, C, c->Cb[c->iC]))) return rc;
+    CK(cudaStreamSynchronize(c->stream));
+    return PDEODE_OK;
+}
+
+namespace {
+// rows of this slab a frame with this filter contains: global rows gi, gi % filter == 0
+void frame_rows(const pdeode_ctx *c, int filter, int *first, int *nro, int *nco) {
+    const int r0 = c->g.row0, r1 = c->g.row0 + c->g.rows;
+    const int f = ((r0 + filter - 1) / filter) * filter;
+    *first = f;
+    *nro = f < r1 ? (r1 - 1 - f) / filter + 1 : 0;
+    *nco = (c->g.col - 1) / filter + 1;
+}
+int frame_buffer(pdeode_ctx *c, size_t doubles) {
+    if (doubles <= c->frame_cap) return PDEODE_OK;
+    if (c->frame_buf) cudaFree(c->frame_buf);
+    c->frame_buf = nullptr; c->frame_cap = 0;
+    CK(cudaMalloc(&c->frame_buf, doubles * sizeof(double)));
+    c->frame_cap = doubles;
+    return PDEODE_OK;
+}
+}  // namespace
+
+int pdeode_frame_size(const pdeode_ctx *c, int filter, int *nrows_out, int *ncols_out) {
+    if (!c || filter < 1) return PDEODE_ERR_ARG;
+    int first, nro, nco;
+    frame_rows(c, filter, &first, &nro, &nco);
+    if (nrows_out) *nrows_out = nro;
+    if (ncols_out) *ncols_out = nco;
+    return PDEODE_OK;
+}
+
+int pdeode_get_frame(pdeode_ctx *c, int filter, double *M, double *C) {
+    if (!c || !M || !C || filter < 1) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int first, nro, nco;
+    frame_rows(c, filter, &first, &nro, &nco);
+    const size_t n = (size_t)nro * nco;
+    if (n == 0) return PDEODE_OK;
+    int rc = frame_buffer(c, 2 * n);
+    if (rc) return rc;
+    CK(launch_decimate(c->g, c->Mb[c->iM], c->Cb[c->iC], filter, first, nro, nco, c->frame_buf,
+                       c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(M, c->frame_buf, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(C, c->frame_buf + n, n * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaStreamSynchronize(c->stream));
+    return PDEODE_OK;
+}
+
+int pdeode_get_frame_rowmeans(pdeode_ctx *c, int filter, double *meanM, double *meanC) {
+    if (!c || !meanM || !meanC || filter < 1) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int first, nro, nco;
+    frame_rows(c, filter, &first, &nro, &nco);
+    if (nro == 0) return PDEODE_OK;
+    int rc = frame_buffer(c, 2 * (size_t)nro);
+    if (rc) return rc;
+    CK(launch_rowmeans(c->g, c->Mb[c->iM], c->Cb[c->iC], filter, first, nro, c->frame_buf, c->stream));
+    c->launches++;
+    CK(cudaMemcpyAsync(meanM, c->frame_buf, nro * sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+    CK(cudaMemcpyAsync(meanC, c->frame_buf + nro, nro * sizeof(double), cudaMemcpyDeviceToHost,
+                       c->stream));
     CK(cudaStreamSynchronize(c->stream));
     return PDEODE_OK;
 }

@@ -1105,7 +1105,56 @@ __global__ void __launch_bounds__(256) k_mass(const MassArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- frame decimation
+
+// What printToFile writes (P:834-842): every filter-th row and column.  One
+// thread per written point; out = [M frame | C frame], nro x nco each.
+__global__ void __launch_bounds__(256) k_decimate(GridDesc g, const double *__restrict__ M,
+                                                  const double *__restrict__ C, int filter,
+                                                  int first_row, int nro, int nco,
+                                                  double *__restrict__ out) {
+    const long long n = (long long)nro * nco;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int oi = (int)(t / nco), oj = (int)(t - (long long)oi * nco);
+        const long long src = (long long)(first_row - g.row0 + oi * filter) * g.P + (long long)oj * filter;
+        out[t] = M[src];
+        out[n + t] = C[src];
+    }
+}
+
+// What printToFile2D writes (P:898-925): for every filter-th row the mean over
+// the columns, added left to right as the reference does.  One thread per row
+// (the layout that uses this has col = 4).  out = [mean M | mean C].
+__global__ void __launch_bounds__(128) k_rowmeans(GridDesc g, const double *__restrict__ M,
+                                                  const double *__restrict__ C, int filter,
+                                                  int first_row, int nro, double *__restrict__ out) {
+    const int oi = blockIdx.x * blockDim.x + threadIdx.x;
+    if (oi >= nro) return;
+    const double *m = M + (long long)(first_row - g.row0 + oi * filter) * g.P;
+    const double *c = C + (long long)(first_row - g.row0 + oi * filter) * g.P;
+    double am = 0.0, ac = 0.0;
+    for (int j = 0; j < g.col; ++j) { am = am + m[j]; ac = ac + c[j]; }   // P:908-909
+    out[oi] = am / g.col;                                                 // P:923
+    out[nro + oi] = ac / g.col;                                           // P:924
+}
+
 }  // namespace
+
+cudaError_t launch_decimate(const GridDesc &g, const double *M, const double *C, int filter,
+                            int first_row, int nro, int nco, double *out, cudaStream_t st) {
+    const long long n = (long long)nro * nco;
+    const int nb = (int)((n + 255) / 256 < 2048 ? (n + 255) / 256 : 2048);
+    k_decimate<<<nb > 0 ? nb : 1, 256, 0, st>>>(g, M, C, filter, first_row, nro, nco, out);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_rowmeans(const GridDesc &g, const double *M, const double *C, int filter,
+                            int first_row, int nro, double *out, cudaStream_t st) {
+    k_rowmeans<<<(nro + 127) / 128 > 0 ? (nro + 127) / 128 : 1, 128, 0, st>>>(g, M, C, filter,
+                                                                               first_row, nro, out);
+    return cudaGetLastError();
+}
 
 // ---------------------------------------------------------------- launchers
 
