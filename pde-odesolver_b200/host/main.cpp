@@ -19,6 +19,9 @@ int main() {
     st.peak = pdeode_peak;
     st.destroy = pdeode_destroy;
     st.strerror_ = pdeode_strerror;
+    st.frame_size = pdeode_frame_size;
+    st.get_frame = pdeode_get_frame;
+    st.get_frame_rowmeans = pdeode_get_frame_rowmeans;
     int device = 0;
     if (const char *d = getenv("PDEODE_DEVICE")) device = atoi(d);
     return pdeode_host::run_program(stdin, stdout, st, device, "");

@@ -286,6 +286,31 @@ void print_to_file_2d(FILE *f, const RunParams &p, const double *M, const double
     put(f, "");                                                                  // P:930
 }
 
+// The same two frames from data already decimated on the device
+// (pdeode_get_frame / pdeode_get_frame_rowmeans): nro x nco points, point
+// (oi, oj) being cell (oi*filter, oj*filter).
+void print_frame(FILE *f, const RunParams &p, int nro, int nco, const double *Md, const double *Cd) {
+    const int filter = frame_filter(p.row);
+    for (int oi = 0; oi < nro; ++oi) {
+        for (int oj = 0; oj < nco; ++oj) {
+            std::string s = fmt_real((double)(oj * filter) / (double)(p.col - 1)) +
+                            fmt_real((double)(oi * filter) / (double)(p.row - 1)) +
+                            fmt_real(Md[(size_t)oi * nco + oj]) + fmt_real(Cd[(size_t)oi * nco + oj]);
+            put(f, s);
+        }
+        put(f, "  ");
+    }
+    put(f, "");
+}
+
+void print_frame_2d(FILE *f, const RunParams &p, int nro, const double *meanM, const double *meanC) {
+    const int filter = frame_filter(p.row);
+    for (int oi = 0; oi < nro; ++oi)
+        fprintf(f, "%20.12f%20.12f%20.12f\n", (double)(oi * filter) / (double)(p.row - 1), meanM[oi],
+                meanC[oi]);
+    put(f, "");
+}
+
 bool report_stats(const std::string &path, double avgIters, double maxIters, double avgNit,
                   double maxNit, double seconds) {
     FILE *f = fopen(path.c_str(), "w");                                          // P:1025-1027
@@ -354,6 +379,7 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
 
     const auto t0 = std::chrono::steady_clock::now();
     bool have_host_copy = true;            // M, C on the host equal the device state
+    std::vector<double> fbufM, fbufC;      // decimated frame data
     while ((double)counter * tDel <= tEnd) {                                     // P:663
         if (counter % (long long)(filter / 100 + 1) == 0) {                      // P:665
             if ((rc = st.mass(ctx, &totalMassM, &totalMassC))) { close_all(); return fail("pdeode_mass"); }
@@ -368,15 +394,31 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
             }
         }
         if (counter % filter == 0) {                                             // P:683
-            if (!have_host_copy) {
-                if ((rc = st.get_state(ctx, M.data(), C.data()))) { close_all(); return fail("pdeode_get_state"); }
-                have_host_copy = true;
-            }
             if (!fframe)
                 fframe = fopen(join(outdir, p.true2D == 1 ? "2D_output.dat" : "output.dat").c_str(), "w");
-            if (fframe) {
-                if (p.true2D == 1) print_to_file_2d(fframe, p, M.data(), C.data());
-                else print_to_file(fframe, p, M.data(), C.data());
+            if (st.frame_size && st.get_frame && st.get_frame_rowmeans) {
+                // only the points a frame contains cross the bus
+                int nro = 0, nco = 0;
+                const int filter = frame_filter(p.row);
+                if ((rc = st.frame_size(ctx, filter, &nro, &nco))) { close_all(); return fail("pdeode_frame_size"); }
+                fbufM.resize((size_t)nro * (p.true2D == 1 ? 1 : nco));
+                fbufC.resize(fbufM.size());
+                if (p.true2D == 1) rc = st.get_frame_rowmeans(ctx, filter, fbufM.data(), fbufC.data());
+                else rc = st.get_frame(ctx, filter, fbufM.data(), fbufC.data());
+                if (rc) { close_all(); return fail("pdeode_get_frame"); }
+                if (fframe) {
+                    if (p.true2D == 1) print_frame_2d(fframe, p, nro, fbufM.data(), fbufC.data());
+                    else print_frame(fframe, p, nro, nco, fbufM.data(), fbufC.data());
+                }
+            } else {
+                if (!have_host_copy) {
+                    if ((rc = st.get_state(ctx, M.data(), C.data()))) { close_all(); return fail("pdeode_get_state"); }
+                    have_host_copy = true;
+                }
+                if (fframe) {
+                    if (p.true2D == 1) print_to_file_2d(fframe, p, M.data(), C.data());
+                    else print_to_file(fframe, p, M.data(), C.data());
+                }
             }
             rs.frames++;
             if (counter == 0)                                                    // P:690-692
@@ -412,6 +454,23 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
     // the final state is never written by the reference (P:747-755); the host
     // arrays are still refreshed, as solveOrder2's intent(out) M, C would be
     rc = st.get_state(ctx, M.data(), C.data());
+    if (const char *fs = getenv("PDEODE_FINAL_STATE")) {
+        // the "Print final solution" the reference has commented out (P:747-755), at
+        // full resolution so that MinitialCond = 11 can continue from it
+        FILE *ff = fopen(join(outdir, fs).c_str(), "w");
+        if (ff) {
+            for (int i = 1; i <= p.row; ++i) {
+                for (int j = 1; j <= p.col; ++j) {
+                    const size_t q = (size_t)j + (size_t)(i - 1) * p.col;
+                    put(ff, fmt_real((double)(j - 1) / (double)(p.col - 1)) +
+                                fmt_real((double)(i - 1) / (double)(p.row - 1)) + fmt_real(M[q - 1]) +
+                                fmt_real(C[q - 1]));
+                }
+                put(ff, "  ");
+            }
+            fclose(ff);
+        }
+    }
     const auto t1 = std::chrono::steady_clock::now();
     close_all();
     st.destroy(ctx);
@@ -477,6 +536,25 @@ int run_program(FILE *in, FILE *con, const Stepper &st, int device, const std::s
     else seed = (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // clock, as init_random_seed.f90:11
     std::vector<double> C, M;
     set_initial_conditions(C, M, p, seed);
+    if (p.MinitialCond == 11) {
+        // The restart the reference's author sketched and left commented out as
+        // "CANNOT GET WORKING" (P:423-435): continue from a previous run's state.
+        // initialCond.dat holds one "x y M C" line per cell in printToFile's order
+        // (blank separator lines ignored), e.g. the file PDEODE_FINAL_STATE writes.
+        std::ifstream f(join(outdir, "initialCond.dat"));
+        std::string line;
+        long long k = 0;
+        while (f && k < p.n && std::getline(f, line)) {
+            std::istringstream is(line);
+            double x, y, m, c;
+            if (is >> x >> y >> m >> c) { M[(size_t)k] = m; C[(size_t)k] = c; ++k; }
+        }
+        if (k != p.n) {
+            say("[!] initialCond.dat: expected " + std::to_string(p.n) + " cells, read " + std::to_string(k));
+            return 2;
+        }
+        say("    M, C continue from initialCond.dat");
+    }
     say("    C = 1");                                                            // P:139
     if (p.MinitialCond == 1) say("    M has non-homogenous Initial Conditions");
     else if (p.MinitialCond == 2) {

@@ -56,6 +56,9 @@ std::string fmt_int(long long v);
 // printToFile (P:810-849) / printToFile2D (P:871-933): append one frame.
 void print_to_file(FILE *f, const RunParams &p, const double *M, const double *C);
 void print_to_file_2d(FILE *f, const RunParams &p, const double *M, const double *C);
+// The same frames from data decimated on the device (pdeode_get_frame*).
+void print_frame(FILE *f, const RunParams &p, int nro, int nco, const double *Md, const double *Cd);
+void print_frame_2d(FILE *f, const RunParams &p, int nro, const double *meanM, const double *meanC);
 // reportStats (P:1019-1040)
 bool report_stats(const std::string &path, double avgIters, double maxIters, double avgNit,
                   double maxNit, double seconds);
@@ -70,6 +73,11 @@ struct Stepper {
     int (*peak)(pdeode_ctx *, double *, double *, double *);
     int (*destroy)(pdeode_ctx *);
     const char *(*strerror_)(int);
+    // optional (may be null): frame data decimated on the device; without them the
+    // host downloads the whole fields at frame times
+    int (*frame_size)(const pdeode_ctx *, int, int *, int *);
+    int (*get_frame)(pdeode_ctx *, int, double *, double *);
+    int (*get_frame_rowmeans)(pdeode_ctx *, int, double *, double *);
 };
 
 struct RunStats {

@@ -78,6 +78,9 @@ def _lib():
         "pdeode_set_state": [vp, vp, vp],
         "pdeode_get_state": [vp, vp, vp],
         "pdeode_step": [vp, ip, llp, llp],
+        "pdeode_frame_size": [vp, C.c_int, ip, ip],
+        "pdeode_get_frame": [vp, C.c_int, vp, vp],
+        "pdeode_get_frame_rowmeans": [vp, C.c_int, vp, vp],
         "pdeode_mass": [vp, dp, dp],
         "pdeode_peak": [vp, dp, dp, dp],
         "pdeode_set_maxit": [vp, C.c_longlong],
@@ -187,6 +190,22 @@ class Solver:
 
     def get_state_ptr(self, m_ptr, c_ptr):
         self._ck(self.lib.pdeode_get_state(self.h, C.c_void_p(m_ptr), C.c_void_p(c_ptr)), "get_state")
+
+    def frame(self, filter_):
+        """Decimated M, C of this slab, as printToFile writes them (P:834-842)."""
+        nr, nc = C.c_int(), C.c_int()
+        self._ck(self.lib.pdeode_frame_size(self.h, filter_, C.byref(nr), C.byref(nc)), "frame_size")
+        M = np.empty((nr.value, nc.value)); Cc = np.empty((nr.value, nc.value))
+        self._ck(self.lib.pdeode_get_frame(self.h, filter_, _ptr(M), _ptr(Cc)), "get_frame")
+        return M, Cc
+
+    def frame_rowmeans(self, filter_):
+        """Per-row column means, as printToFile2D writes them (P:898-925)."""
+        nr, nc = C.c_int(), C.c_int()
+        self._ck(self.lib.pdeode_frame_size(self.h, filter_, C.byref(nr), C.byref(nc)), "frame_size")
+        m = np.empty(nr.value); c = np.empty(nr.value)
+        self._ck(self.lib.pdeode_get_frame_rowmeans(self.h, filter_, _ptr(m), _ptr(c)), "rowmeans")
+        return m, c
 
     def step(self):
         cnt, s, mx = C.c_int(), C.c_longlong(), C.c_longlong()

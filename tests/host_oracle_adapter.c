@@ -75,9 +75,13 @@ typedef struct {
     int (*peak)(pdeode_ctx *, double *, double *, double *);
     int (*destroy)(pdeode_ctx *);
     const char *(*strerror_)(int);
+    /* optional device-side frame decimation: absent here, so the host takes its
+     * whole-field writer path -- the GPU run takes the other, and the two are compared */
+    void *frame_size, *get_frame, *get_frame_rowmeans;
 } stepper_table;
 
 static const stepper_table TABLE = {a_create, a_set_state, a_get_state, a_step,
-                                    a_mass,   a_peak,      a_destroy,   a_strerror};
+                                    a_mass,   a_peak,      a_destroy,   a_strerror,
+                                    0,        0,           0};
 
 const void *oracle_stepper_table(void) { return &TABLE; }

@@ -384,3 +384,25 @@ def test_set_state_resets_warm_start(pb):
     assert a["nits"] == b["nits"]
     assert np.array_equal(Ma, Mb) and np.array_equal(Ca, Cb)
     s.close()
+
+
+# ------------------------------------------------------------ device-side frame decimation
+
+@pytest.mark.parametrize("row,col,filt", [(33, 33, 1), (1025, 1025, 4), (513, 300, 2), (1025, 4, 4)])
+def test_frames_decimated_on_device(pb, row, col, filt):
+    """pdeode_get_frame / pdeode_get_frame_rowmeans return exactly what
+    printToFile / printToFile2D read out of the whole fields (P:834-842, P:898-925)."""
+    rng = np.random.RandomState(row + col)
+    M0 = rng.rand(row * col); C0 = rng.rand(row * col)
+    s = pb.Solver(row, col, pb.default_params(row))
+    s.set_state(M0, C0)
+    Md, Cd = s.frame(filt)
+    assert np.array_equal(Md, M0.reshape(row, col)[::filt, ::filt])
+    assert np.array_equal(Cd, C0.reshape(row, col)[::filt, ::filt])
+    mm, mc = s.frame_rowmeans(filt)
+    want = np.zeros(len(range(0, row, filt)))
+    for j in range(col):                      # left-to-right sum, as P:908
+        want = want + M0.reshape(row, col)[::filt, j]
+    assert np.array_equal(mm, want / col)
+    assert mc == pytest.approx(C0.reshape(row, col)[::filt].mean(axis=1), rel=1e-14)
+    s.close()

@@ -227,6 +227,44 @@ def test_whole_program_with_oracle_stepper(host, adapter, tmp_path):
     assert avg_nit == pytest.approx(sumN / sumP, rel=1e-15)
 
 
+def test_final_state_and_restart(host, adapter, tmp_path, monkeypatch):
+    """PDEODE_FINAL_STATE writes the final fields (the print the reference has
+    commented out, P:747-755); MinitialCond = 11 continues from such a file (the
+    restart the reference could not get working, P:423-435)."""
+    base = open(os.path.join(DATA, "wave2d.txt")).read()
+    full = tmp_path / "full"; a = tmp_path / "a"; b = tmp_path / "b"
+    for d in (full, a, b):
+        d.mkdir()
+    # 41 steps in one go
+    (tmp_path / "full.txt").write_text(base)
+    monkeypatch.setenv("PDEODE_FINAL_STATE", "final.dat")
+    assert host.pdeode_host_run(str(tmp_path / "full.txt").encode(), str(full).encode(),
+                                str(tmp_path / "c0.txt").encode(), adapter.oracle_stepper_table(), 0) == 0
+    # 21 steps, then 20 more from the written state
+    (tmp_path / "first.txt").write_text(base.replace("tEnd      = 0.04", "tEnd      = 0.0205")
+                                        .replace("nOuts     = 4", "nOuts     = 2"))
+    assert host.pdeode_host_run(str(tmp_path / "first.txt").encode(), str(a).encode(),
+                                str(tmp_path / "c1.txt").encode(), adapter.oracle_stepper_table(), 0) == 0
+    fin = np.loadtxt(a / "final.dat")
+    assert fin.shape == (129 * 4, 4)
+    os.rename(a / "final.dat", b / "initialCond.dat")
+    (tmp_path / "second.txt").write_text(base.replace("tEnd      = 0.04", "tEnd      = 0.0195")
+                                         .replace("nOuts     = 4", "nOuts     = 1")
+                                         .replace("MinitialCond = 1", "MinitialCond = 11"))
+    assert host.pdeode_host_run(str(tmp_path / "second.txt").encode(), str(b).encode(),
+                                str(tmp_path / "c2.txt").encode(), adapter.oracle_stepper_table(), 0) == 0
+    assert "continue from initialCond.dat" in open(tmp_path / "c2.txt").read()
+    want = np.loadtxt(full / "final.dat")
+    got = np.loadtxt(b / "final.dat")
+    # same trajectory; the restart only loses the CG warm start of its first solve
+    assert np.allclose(got[:, 2:], want[:, 2:], rtol=0, atol=2e-7)
+    assert np.array_equal(got[:, :2], want[:, :2])
+    # a wrong-size file is refused
+    (b / "initialCond.dat").write_text("0 0 0.5 1\n")
+    assert host.pdeode_host_run(str(tmp_path / "second.txt").encode(), str(b).encode(),
+                                str(tmp_path / "c3.txt").encode(), adapter.oracle_stepper_table(), 0) == 2
+
+
 def test_gfortran_shim_creates_a_out(tmp_path):
     ge.build_cuda(); ge.build_host()
     shim = os.path.join(ge.PKG, "scripts", "gfortran")
