@@ -140,6 +140,7 @@ struct UpdateArgs {
     const double *p, *q;
     long long n2;          // number of double2 elements to stream (rows*P/2)
     int fuse_scalars;
+    int reverse;           // 1: sweep high -> low addresses (L2 reuse against the SpMV kernel)
     long long seq;
     NumParams np;          // SUMS_PEER: the stop test runs in this kernel's last CTA
     double *trace;
@@ -194,6 +195,7 @@ struct LaunchCfg {
     // persistent CG solve: 0 = off, else one cooperative launch per solve with
     // p_nstrips * p_nchunks CTAs of p_BS consumer threads
     int persist, p_BS, p_nstrips, p_nchunks;
+    int kb_reverse;        // K_B sweeps against K_A's direction
 };
 cudaError_t launch_cg_persist(const PersistArgs &a, int BS, cudaStream_t st);
 // Heuristic defaults for a grid, then PDEODE_BS / PDEODE_TR / PDEODE_DEPTH /

@@ -199,6 +199,7 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     u.x = x; u.r = c->r; u.p = c->p; u.q = c->q;
     u.n2 = (long long)c->g.rows * c->g.P / 2;
     u.fuse_scalars = mode;
+    u.reverse = c->cfg.kb_reverse;
     u.seq = c->seq;
     u.np = c->np; u.trace = a.trace; u.pc = c->pc;
     u.wait_phase = c->phase;                 // posted by the K_A just launched
@@ -941,6 +942,7 @@ int pdeode_time_kernel(pdeode_ctx *c, int kernel, int reps, float *ms_per_launch
     UpdateArgs u{};
     u.g = c->g; u.S = c->S; u.partials = c->partials; u.x = c->Mb[(c->iM + 1) % 3]; u.r = c->r;
     u.p = c->p; u.q = c->q; u.n2 = (long long)c->g.rows * c->g.P / 2; u.fuse_scalars = 0;
+    u.reverse = c->cfg.kb_reverse;
     SolveCArgs sc{};
     sc.g = c->g; sc.np = c->np; sc.S = c->S; sc.partials = c->partials;
     sc.Mprev = c->Mb[c->iM]; sc.Mnew = c->Mb[(c->iM + 1) % 3]; sc.Cprev = c->Cb[c->iC];

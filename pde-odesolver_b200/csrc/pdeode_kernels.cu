@@ -27,7 +27,7 @@ namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
 
-int g_stream_ctas_per_sm = 8;
+int g_stream_ctas_per_sm = 16;   // grid of the streaming kernels, in CTAs per SM
 int g_num_sms = 148;
 
 // ---------------------------------------------------------------- helpers
@@ -766,10 +766,14 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         if (dn && k >= last_row0) st2(dn + k, v);
     };
     double rr = 0.0, xx = 0.0;
+    const bool rev = a.reverse != 0;
     const long long stride = (long long)gridDim.x * blockDim.x;
     long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     for (; i + stride < a.n2; i += 2 * stride) {
-        const long long k0 = 2 * i, k1 = 2 * (i + stride);
+        // reverse: sweep from the high addresses down, i.e. start where the SpMV kernel
+        // just finished, so that the tails of p, q, r it left in L2 are hit
+        const long long k0 = 2 * (rev ? a.n2 - 1 - i : i);
+        const long long k1 = 2 * (rev ? a.n2 - 1 - (i + stride) : i + stride);
         double2 x0 = ld2(a.x + k0), p0 = ld2(a.p + k0), r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
         double2 x1 = ld2(a.x + k1), p1 = ld2(a.p + k1), r1 = ld2(a.r + k1), q1 = ld2(a.q + k1);
         x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
@@ -782,7 +786,7 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         xx += x0.x * x0.x; xx += x0.y * x0.y; xx += x1.x * x1.x; xx += x1.y * x1.y;
     }
     for (; i < a.n2; i += stride) {
-        const long long k0 = 2 * i;
+        const long long k0 = 2 * (rev ? a.n2 - 1 - i : i);
         double2 x0 = ld2(a.x + k0), p0 = ld2(a.p + k0), r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
         x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
         r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
@@ -1250,9 +1254,17 @@ LaunchCfg launch_config(const GridDesc &g) {
     if (nch > by_rows) nch = by_rows;
     c.p_nchunks = nch;
     // default: where a CG iteration is short enough for launch latency to matter
+    // (measured: one GPU, faster up to 2048^2 and 4 % slower at 4096^2; as a slab of a
+    // multi-GPU run, where every kernel boundary also waits for the peers, still 11 %
+    // faster at 8.4M cells per GPU)
     const long long cells = (long long)g.rows * g.P;
-    c.persist = (nch >= 1 && c.variant == 1 && cells <= (4LL << 20)) ? 1 : 0;
+    const long long limit = (g.rows != g.grow) ? (16LL << 20) : (4LL << 20);
+    c.persist = (nch >= 1 && c.variant == 1 && cells <= limit) ? 1 : 0;
     if (const char *e = getenv("PDEODE_PERSIST")) c.persist = (atoi(e) != 0 && nch >= 1) ? 1 : 0;
+    // measured at 4096^2 (bench.py): 6.29e10 with the reverse sweep and 16 CTAs per SM
+    // against 5.95e10 forward with 8
+    c.kb_reverse = 1;
+    if (const char *e = getenv("PDEODE_KB_REVERSE")) c.kb_reverse = atoi(e) != 0;
     return c;
 }
 
