@@ -99,6 +99,17 @@ int pdeode_set_stream(pdeode_ctx *ctx, void *cuda_stream);
  * solveOrder2 would (P:133-138, P:623). */
 int pdeode_set_state(pdeode_ctx *ctx, const double *M, const double *C);
 
+/* setInitialConditions on the device (P:262-439), instead of
+ * generating the fields on the host and uploading them.  MinitialCond 1-6 and
+ * 8-10; 7 (one random draw per cell, in sequence) is not offered -- generate it
+ * on the host and use pdeode_set_state.  px, py: the npts inoculation points of
+ * cases 4, 5, 9, 10 (the caller's random draws xr, yr of P:312-313, 332-334,
+ * 409-414, or the spacing of P:393 with py = 0); ignored otherwise.  Same
+ * values as the reference's loops, cell by cell; case 5's normalisation sums
+ * in parallel.  Resets the CG warm start like pdeode_set_state. */
+int pdeode_set_initial_condition(pdeode_ctx *ctx, int MinitialCond, double depth, double height,
+                                 int npts, const double *px, const double *py);
+
 /* D2H of this context's slab; needed at frame times only (P:685-687). */
 int pdeode_get_state(pdeode_ctx *ctx, double *M, double *C);
 

@@ -177,6 +177,13 @@ cudaError_t launch_stencil_cg(const StencilArgs &a, cudaStream_t st);
 cudaError_t launch_update(const UpdateArgs &a, cudaStream_t st);
 cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st);
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t st);
+cudaError_t launch_init_cond(const GridDesc &g, int ic, double depth, double height, double xDel,
+                             int npts, const double *px, const double *py, double *M, double *C,
+                             cudaStream_t st);
+cudaError_t launch_ic_count_sum(const GridDesc &g, const double *M, DevScal *S, double *partials,
+                                cudaStream_t st);
+cudaError_t launch_ic_scale(const GridDesc &g, double *M, const DevScal *S, double height,
+                            cudaStream_t st);
 cudaError_t launch_decimate(const GridDesc &g, const double *M, const double *C, int filter,
                             int first_row, int nro, int nco, double *out, cudaStream_t st);
 cudaError_t launch_rowmeans(const GridDesc &g, const double *M, const double *C, int filter,

@@ -657,6 +657,42 @@ int pdeode_set_state(pdeode_ctx *c, const double *M, const double *C) {
     return PDEODE_OK;
 }
 
+int pdeode_set_initial_condition(pdeode_ctx *c, int ic, double depth, double height, int npts,
+                                 const double *px, const double *py) {
+    if (!c || ic < 1 || ic > 10 || ic == 7) return PDEODE_ERR_ARG;
+    const bool pts = (ic == 4 || ic == 5 || ic == 9 || ic == 10);
+    if (pts && (npts < 0 || (npts > 0 && (!px || !py)))) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    c->iM = c->iMprev = 0; c->iC = c->iCprev = 0; c->iMnew = 1;
+    double *dp = nullptr;
+    if (pts && npts > 0) {
+        CK(cudaMalloc(&dp, sizeof(double) * 2 * (size_t)npts));
+        CK(cudaMemcpyAsync(dp, px, sizeof(double) * (size_t)npts, cudaMemcpyHostToDevice, c->stream));
+        CK(cudaMemcpyAsync(dp + npts, py, sizeof(double) * (size_t)npts, cudaMemcpyHostToDevice,
+                           c->stream));
+    }
+    CK(launch_init_cond(c->g, ic, depth, height, c->params.xDel, dp ? npts : 0, dp,
+                        dp ? dp + npts : nullptr, c->Mb[0], c->Cb[0], c->stream));
+    c->launches++;
+    if (ic == 5) {                                   // P:343-352
+        CK(launch_ic_count_sum(c->g, c->Mb[0], c->S, c->partials, c->stream));
+        c->launches++;
+        if (multi(c)) {
+            int rc = allreduce_part(c, 2);
+            if (rc) return rc;
+        }
+        CK(launch_ic_scale(c->g, c->Mb[0], c->S, height, c->stream));
+        c->launches++;
+    }
+    int rc = zero_array(c, 1);                       // Mnew := 0, the first warm start (D8)
+    if (rc) return rc;
+    c->warm = false;
+    c->mass_valid = false;
+    CK(cudaStreamSynchronize(c->stream));
+    if (dp) CK(cudaFree(dp));
+    return PDEODE_OK;
+}
+
 int pdeode_get_state(pdeode_ctx *c, double *M, double *C) {
     if (!c || !M || !C) return PDEODE_ERR_ARG;
     CK(cudaSetDevice(c->device));

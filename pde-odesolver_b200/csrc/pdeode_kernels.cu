@@ -1143,7 +1143,117 @@ __global__ void __launch_bounds__(128) k_rowmeans(GridDesc g, const double *__re
     out[nro + oi] = ac / g.col;                                           // P:924
 }
 
+// ---------------------------------------------------------------- initial conditions on the device
+
+// setInitialConditions (P:262-439) cell by cell.  The cases that loop over
+// inoculation points (4, 5, 9, 10) cost O(n * points) on the host -- 1.6e10
+// point evaluations at 16384^2 with the shipped 60 points; here
+// every cell walks the point list itself, in the reference's order, so the
+// values are the host's bit for bit.  px / py hold the points: the random
+// draws of P:312-313,332-334,409-414 (made by the caller's seeded generator)
+// or the spacing formula of P:393.  Case 7 draws one random number per cell
+// in sequence and stays on the host.
+__global__ void __launch_bounds__(256) k_init_cond(GridDesc g, int ic, double depth, double height,
+                                                   double xDel, int npts,
+                                                   const double *__restrict__ px,
+                                                   const double *__restrict__ py,
+                                                   double *__restrict__ M, double *__restrict__ C) {
+    const long long n_loc = (long long)g.rows * g.P;
+    const long long n = (long long)g.grow * g.col;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_loc;
+         t += (long long)gridDim.x * blockDim.x) {
+        const int li = (int)(t / g.P), j = (int)(t - (long long)li * g.P);
+        if (j >= g.col) { M[t] = 0.0; C[t] = 0.0; continue; }
+        const long long i = (long long)(g.row0 + li) * g.col + j + 1;     // the reference's 1-based cell
+        double m = 0.0;                                                   // P:276
+        if (ic == 1) {                                                    // P:279-288
+            const double a = -height / ((depth * depth) * (depth * depth));
+            const long long x = (i - 1) / g.col;
+            const double tt = (double)x * xDel;
+            const double f = a * ((tt * tt) * (tt * tt)) + height;
+            m = (f <= 0) ? 0.0 : f;
+        } else if (ic == 2) {                                             // P:291-292
+            m = height;
+        } else if (ic == 3) {                                             // P:295-305
+            const double a = -height / (depth * depth);
+            const long long x = i % g.col, y = i / g.grow;
+            const double u = x * xDel - 0.5, v = y * xDel - 0.5;
+            const double f = a * (u * u + v * v) + height;
+            m = (f <= 0) ? 0.0 : f;
+        } else if (ic == 4 || ic == 9) {                                  // P:308-325, P:390-402
+            const double a = -height / (depth * depth);
+            const long long x = i % g.col, y = i / g.grow;
+            for (int k = 0; k < npts; ++k) {
+                if (m <= 0) {
+                    const double u = x * xDel - px[k], v = y * xDel - py[k];
+                    m = m + a * (u * u + v * v) + height;
+                    if (m <= 0) m = 0;
+                }
+            }
+        } else if (ic == 5 || ic == 10) {                                 // P:328-341, P:405-421
+            const double a = -height / (depth * depth);
+            const long long x = i % g.col, y = i / g.grow;
+            for (int k = 0; k < npts; ++k) {
+                const double u = x * xDel - px[k], v = y * xDel - py[k];
+                const double innoc = a * (u * u + v * v) + height;
+                if (innoc >= 0) m = m + innoc;
+            }
+        } else if (ic == 6) {                                             // P:356-362
+            const long long x = (i - 1) / g.col;
+            if (x * xDel <= depth) m = height;
+        } else if (ic == 8) {                                             // P:375-387
+            m = (double)i / (double)n / 4.0;
+            if (m >= 0.1) m = 0;
+        }
+        M[t] = m;
+        C[t] = 1.0;                                                       // P:276
+    }
+}
+
+// P:343-349: number and sum of the cells with M > 0 (case 5's normalisation)
+__global__ void __launch_bounds__(256) k_ic_count_sum(GridDesc g, const double *__restrict__ M,
+                                                      DevScal *S, double *partials) {
+    __shared__ double sm[64];
+    const long long n_loc = (long long)g.rows * g.P;
+    double cnt = 0.0, tot = 0.0;
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_loc;
+         t += (long long)gridDim.x * blockDim.x) {
+        const double m = M[t];
+        if (m > 0) { cnt += 1.0; tot += m; }
+    }
+    if (grid_sum2(cnt, tot, partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_MASS], sm)) {
+        S->part[0] = cnt; S->part[1] = tot;
+    }
+}
+
+// P:350-352: M(j) = M(j) * height/(total/real(i)), factor from S->part (all ranks' sums)
+__global__ void __launch_bounds__(256) k_ic_scale(GridDesc g, double *__restrict__ M, const DevScal *S,
+                                                  double height) {
+    const long long n_loc = (long long)g.rows * g.P;
+    const double denom = S->part[1] / S->part[0];
+    for (long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x; t < n_loc;
+         t += (long long)gridDim.x * blockDim.x)
+        M[t] = M[t] * height / denom;
+}
+
 }  // namespace
+
+cudaError_t launch_init_cond(const GridDesc &g, int ic, double depth, double height, double xDel,
+                             int npts, const double *px, const double *py, double *M, double *C,
+                             cudaStream_t st) {
+    k_init_cond<<<stream_blocks(), 256, 0, st>>>(g, ic, depth, height, xDel, npts, px, py, M, C);
+    return cudaGetLastError();
+}
+cudaError_t launch_ic_count_sum(const GridDesc &g, const double *M, DevScal *S, double *partials,
+                                cudaStream_t st) {
+    k_ic_count_sum<<<296, 256, 0, st>>>(g, M, S, partials);
+    return cudaGetLastError();
+}
+cudaError_t launch_ic_scale(const GridDesc &g, double *M, const DevScal *S, double height,
+                            cudaStream_t st) {
+    k_ic_scale<<<stream_blocks(), 256, 0, st>>>(g, M, S, height);
+    return cudaGetLastError();
+}
 
 cudaError_t launch_decimate(const GridDesc &g, const double *M, const double *C, int filter,
                             int first_row, int nro, int nco, double *out, cudaStream_t st) {

@@ -36,6 +36,7 @@ int main(int argc, char **argv) {
     st.destroy = pdeode_destroy; st.strerror_ = pdeode_strerror;
     st.frame_size = pdeode_frame_size; st.get_frame = pdeode_get_frame;
     st.get_frame_rowmeans = pdeode_get_frame_rowmeans;
+    st.set_initial_condition = pdeode_set_initial_condition;
 
     std::vector<int> devices;
     if (const char *d = getenv("PDEODE_DEVICES")) {

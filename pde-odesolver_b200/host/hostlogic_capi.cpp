@@ -60,6 +60,18 @@ int pdeode_host_initial_conditions(const pdeode_host_params *pp, unsigned long l
     return 0;
 }
 
+// The inoculation points set_initial_conditions uses for this case and seed
+// (what the host hands to pdeode_set_initial_condition).  Returns the count.
+int pdeode_host_inoculation_points(const pdeode_host_params *pp, unsigned long long seed,
+                                   double *px, double *py, int cap) {
+    RunParams p = unflatten(pp);
+    std::vector<double> x, y;
+    inoculation_points(p, seed, x, y);
+    const int n = (int)x.size() < cap ? (int)x.size() : cap;
+    for (int k = 0; k < n; ++k) { px[k] = x[(size_t)k]; py[k] = y[(size_t)k]; }
+    return (int)x.size();
+}
+
 int pdeode_host_format_real(double x, char *out, int len) {
     const std::string s = fmt_real(x);
     strncpy(out, s.c_str(), len - 1);

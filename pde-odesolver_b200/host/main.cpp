@@ -22,6 +22,7 @@ int main() {
     st.frame_size = pdeode_frame_size;
     st.get_frame = pdeode_get_frame;
     st.get_frame_rowmeans = pdeode_get_frame_rowmeans;
+    st.set_initial_condition = pdeode_set_initial_condition;
     int device = 0;
     if (const char *d = getenv("PDEODE_DEVICE")) device = atoi(d);
     return pdeode_host::run_program(stdin, stdout, st, device, "");

@@ -150,6 +150,37 @@ struct Rng {
 
 }  // namespace
 
+// The inoculation points of MinitialCond 4, 5, 9, 10 in the order
+// set_initial_conditions below draws / computes them; handed to
+// pdeode_set_initial_condition so that the device builds the same field.
+bool inoculation_points(const RunParams &p, uint64_t seed, std::vector<double> &px,
+                        std::vector<double> &py) {
+    px.clear(); py.clear();
+    Rng rng{seed};
+    const int ic = p.MinitialCond, np = p.numInnocu;
+    if (ic == 4) {
+        for (int k = 1; k <= np; ++k) { px.push_back(rng.next()); py.push_back(rng.next()); }
+    } else if (ic == 5) {
+        for (int k = 1; k <= np; ++k) { px.push_back(rng.next()); py.push_back(rng.next() * 0.1); }
+    } else if (ic == 9) {
+        for (int k = 1; k <= np; ++k) {
+            px.push_back(p.depth + (k - 1) * 2 * p.depth +
+                         ((k - 1) * (1 - np * p.depth * 2)) / (double)(np - 1));
+            py.push_back(0.0);
+        }
+    } else if (ic == 10) {
+        for (int k = 1; k <= 2 * np; ++k) {
+            px.push_back(rng.next());
+            double yr = rng.next() * 0.1;
+            if (k > np) yr = yr + 0.9;
+            py.push_back(yr);
+        }
+    } else {
+        return false;
+    }
+    return true;
+}
+
 void set_initial_conditions(std::vector<double> &C, std::vector<double> &M, const RunParams &p,
                             uint64_t seed) {
     const long long n = p.n;
@@ -334,7 +365,8 @@ static std::string join(const std::string &dir, const char *name) {
 }
 
 RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<double> &C,
-                      const Stepper &st, int device, const std::string &outdir, FILE *con) {
+                      const Stepper &st, int device, const std::string &outdir, FILE *con,
+                      const DeviceIc *dic) {
     RunStats rs;
     const double tDel = p.tDel, tEnd = p.tEnd;
     const int filter = (int)(tEnd / (p.nOuts * tDel));                           // P:638
@@ -357,7 +389,15 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
         return rs;
     };
     if (rc) return fail("pdeode_create");
-    if ((rc = st.set_state(ctx, M.data(), C.data()))) return fail("pdeode_set_state");
+    const bool device_ic = dic && st.set_initial_condition;
+    if (device_ic) {
+        // the fields are built where they will live: nothing to upload
+        rc = st.set_initial_condition(ctx, dic->ic, dic->depth, dic->height, (int)dic->px.size(),
+                                      dic->px.data(), dic->py.data());
+        if (rc) return fail("pdeode_set_initial_condition");
+    } else if ((rc = st.set_state(ctx, M.data(), C.data()))) {
+        return fail("pdeode_set_state");
+    }
 
     long long counter = 0;                                                       // P:640
     double avgIters = 0, avgNit = 0;                                             // P:642-643
@@ -378,7 +418,7 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
     fprintf(con, "    time    avgIter  maxIter      avgNit  maxNit        avgM        avgC\n");  // P:661
 
     const auto t0 = std::chrono::steady_clock::now();
-    bool have_host_copy = true;            // M, C on the host equal the device state
+    bool have_host_copy = !device_ic;      // M, C on the host equal the device state
     std::vector<double> fbufM, fbufC;      // decimated frame data
     while ((double)counter * tDel <= tEnd) {                                     // P:663
         if (counter % (long long)(filter / 100 + 1) == 0) {                      // P:665
@@ -535,7 +575,20 @@ int run_program(FILE *in, FILE *con, const Stepper &st, int device, const std::s
     if (const char *s = getenv("PDEODE_SEED")) seed = strtoull(s, nullptr, 10);
     else seed = (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // clock, as init_random_seed.f90:11
     std::vector<double> C, M;
-    set_initial_conditions(C, M, p, seed);
+    // Build the fields on the device when the stepper offers it (all cases but the
+    // per-cell random one, 7, and the restart, 11); PDEODE_HOST_IC=1 forces the host loops.
+    DeviceIc dic;
+    const int icn = p.MinitialCond;
+    const bool use_dic = st.set_initial_condition && st.frame_size && icn >= 1 && icn <= 10 && icn != 7 &&
+                         !(getenv("PDEODE_HOST_IC") && getenv("PDEODE_HOST_IC")[0] == '1');
+    if (use_dic) {
+        dic.ic = icn; dic.depth = p.depth; dic.height = p.height;
+        inoculation_points(p, seed, dic.px, dic.py);
+        M.assign((size_t)p.n, 0.0);
+        C.assign((size_t)p.n, 1.0);
+    } else {
+        set_initial_conditions(C, M, p, seed);
+    }
     if (p.MinitialCond == 11) {
         // The restart the reference's author sketched and left commented out as
         // "CANNOT GET WORKING" (P:423-435): continue from a previous run's state.
@@ -562,7 +615,7 @@ int run_program(FILE *in, FILE *con, const Stepper &st, int device, const std::s
         say("        M = " + fmt_real(p.height));
     }
     say("Starting Solver");                                                      // P:148
-    RunStats rs = solve_order2(p, M, C, st, device, outdir, con);
+    RunStats rs = solve_order2(p, M, C, st, device, outdir, con, use_dic ? &dic : nullptr);
     if (rs.status == PDEODE_ERR_PICARD_CAP) return 0;       // Fortran `stop`: exit code 0
     if (rs.status) return 1;
     say("-------------------------------------------------------------");        // P:161-169

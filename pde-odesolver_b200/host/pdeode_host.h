@@ -78,7 +78,19 @@ struct Stepper {
     int (*frame_size)(const pdeode_ctx *, int, int *, int *);
     int (*get_frame)(pdeode_ctx *, int, double *, double *);
     int (*get_frame_rowmeans)(pdeode_ctx *, int, double *, double *);
+    // optional: build the initial fields on the device instead of uploading them
+    int (*set_initial_condition)(pdeode_ctx *, int, double, double, int, const double *,
+                                 const double *);
 };
+
+// What pdeode_set_initial_condition needs: the case and its inoculation points.
+struct DeviceIc {
+    int ic = 0;
+    double depth = 0, height = 0;
+    std::vector<double> px, py;
+};
+bool inoculation_points(const RunParams &p, uint64_t seed, std::vector<double> &px,
+                        std::vector<double> &py);
 
 struct RunStats {
     double avgIters = 0, maxIters = 0, avgNit = 0, maxNit = 0;   // P:76-77
@@ -90,7 +102,8 @@ struct RunStats {
 // solveOrder2 (P:600-763) with the step body replaced by stepper calls.
 // Files are written into outdir ("" = cwd); console goes to `con`.
 RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<double> &C,
-                      const Stepper &st, int device, const std::string &outdir, FILE *con);
+                      const Stepper &st, int device, const std::string &outdir, FILE *con,
+                      const DeviceIc *dic = nullptr);
 
 // program cThermoPDEODE (P:20-175): prompts for the parameter file name on
 // `in`, echoes the setup, runs, reports.  Returns the process exit code.

@@ -77,6 +77,7 @@ def _lib():
         "pdeode_set_stream": [vp, vp],
         "pdeode_set_state": [vp, vp, vp],
         "pdeode_get_state": [vp, vp, vp],
+        "pdeode_set_initial_condition": [vp, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp],
         "pdeode_step": [vp, ip, llp, llp],
         "pdeode_frame_size": [vp, C.c_int, ip, ip],
         "pdeode_get_frame": [vp, C.c_int, vp, vp],
@@ -190,6 +191,13 @@ class Solver:
 
     def get_state_ptr(self, m_ptr, c_ptr):
         self._ck(self.lib.pdeode_get_state(self.h, C.c_void_p(m_ptr), C.c_void_p(c_ptr)), "get_state")
+
+    def set_initial_condition(self, ic, depth, height, px=(), py=()):
+        """setInitialConditions on the device (P:262-439)."""
+        px = np.ascontiguousarray(px, np.float64); py = np.ascontiguousarray(py, np.float64)
+        self._ck(self.lib.pdeode_set_initial_condition(
+            self.h, ic, depth, height, px.size, _ptr(px) if px.size else None,
+            _ptr(py) if py.size else None), "set_initial_condition")
 
     def frame(self, filter_):
         """Decimated M, C of this slab, as printToFile writes them (P:834-842)."""

@@ -97,3 +97,45 @@ def test_ensemble_members_equal_single_runs(tmp_path):
         assert s.returncode == 0
         for name in ("total.dat", "COprod.dat", "output.dat"):
             assert open(out / name).read() == open(single / name).read(), (k, name)
+
+
+@pytest.mark.parametrize("ic", [1, 2, 3, 4, 5, 6, 8, 9, 10])
+@pytest.mark.parametrize("row,col", [(65, 65), (129, 4), (70, 45)])
+def test_initial_conditions_built_on_device(ic, row, col):
+    """pdeode_set_initial_condition against the host's setInitialConditions
+    (P:262-439): same points, same loops, bit-identical fields; case 5's
+    normalisation (a parallel sum) to rounding."""
+    from test_host_program import HostParams
+    ge.build_cuda(); ge.build_host()
+    import pdeode_b200 as pb
+    host = C.CDLL(os.path.join(ge.LIBDIR, "libpdeode_hostlogic.so"))
+    host.pdeode_host_initial_conditions.argtypes = [C.POINTER(HostParams), C.c_ulonglong, C.c_void_p, C.c_void_p]
+    host.pdeode_host_inoculation_points.argtypes = [C.POINTER(HostParams), C.c_ulonglong, C.c_void_p,
+                                                    C.c_void_p, C.c_int]
+    p = HostParams(pSize=row, true2D=int(col == 4), numInnocu=7, MinitialCond=ic, row=row, col=col,
+                   n=row * col, depth=0.2, height=0.3, xDel=1.0 / row)
+    Mh = np.empty(row * col); Ch = np.empty(row * col)
+    host.pdeode_host_initial_conditions(C.byref(p), 42, Mh.ctypes.data, Ch.ctypes.data)
+    px = np.zeros(64); py = np.zeros(64)
+    npts = host.pdeode_host_inoculation_points(C.byref(p), 42, px.ctypes.data, py.ctypes.data, 64)
+    s = pb.Solver(row, col, pb.default_params(row))
+    s.set_initial_condition(ic, 0.2, 0.3, px[:npts], py[:npts])
+    Md, Cd = s.get_state()
+    assert np.array_equal(Cd, Ch)
+    if ic == 5:
+        assert np.allclose(Md, Mh, rtol=1e-14, atol=0)
+    else:
+        assert np.array_equal(Md, Mh)
+    if Mh.max() == 0:          # e.g. the centred blob of case 3 on a 4-column grid: nothing to step
+        s.close()
+        return
+    # and the state steps like an uploaded one
+    s2 = pb.Solver(row, col, pb.default_params(row))
+    s2.set_state(Md, Cd)
+    s.set_maxit(200); s2.set_maxit(200)     # a NaN field never meets the stop test (CG:90)
+    assert s.step()["nitSum"] == s2.step()["nitSum"]
+    a, b = s.get_state(), s2.get_state()
+    # (overlapping blobs can push M past 1, where D(M) is singular and both runs fill with
+    # NaN alike -- the reference's unguarded hazard S8 -- hence equal_nan)
+    assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
+    s.close(); s2.close()
