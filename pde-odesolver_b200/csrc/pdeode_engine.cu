@@ -73,6 +73,8 @@ struct pdeode_ctx {
     void *ipc_open[2 * PEER_MAX_RANKS + 2] = {nullptr};
     int n_ipc_open = 0;
     unsigned long long phase = 0;               // id of the last posting kernel launched
+    bool pending_persist = false;               // a persistent solve is queued, not yet read back
+    int pending_ip0 = 0;
 
     LaunchCfg cfg{256, 64, 4, 1};
     int pred[MAX_PICARD_TRACE];
@@ -251,19 +253,12 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         pa.nstrips = c->cfg.p_nstrips; pa.nchunks = c->cfg.p_nchunks;
         CK(launch_cg_persist(pa, c->cfg.p_BS, c->stream));
         c->launches++;
-        int rc = snapshot(c, 0);
-        if (rc) return rc;
-        if ((rc = wait_snapshot(c, 0))) return rc;
-        const DevScal &fin = c->snap[0].s;
-        if (fin.error) {
-            c->err = "peer exchange timed out (a rank stopped posting)";
-            return PDEODE_ERR_CUDA;
-        }
-        c->phase += 2ULL * (unsigned long long)fin.nit;   // two exchanges per iteration
-        c->ip = ip0 ^ (int)(fin.nit & 1);
-        c->p = c->pbuf[c->ip];
-        *nit_out = fin.nit;
-        *stop_out = fin.stop;
+        // no wait here: the C update queues right behind, and the caller reads the
+        // iteration count out of the same record as the Picard residuals
+        c->pending_persist = true;
+        c->pending_ip0 = ip0;
+        *nit_out = 0;
+        *stop_out = 0;
         return PDEODE_OK;
     }
 
@@ -794,7 +789,6 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         if ((rc = solve(c, x0, c->Mb[inew], count, &nit, &stop))) return rc;
         c->warm = true;
         c->iMnew = inew;
-        if (stop == -1 || stop == -101) warn = PDEODE_WARN_CG_CAP;
 
         int icnew = 0;
         while (icnew == c->iCprev || icnew == c->iC) icnew++;
@@ -816,6 +810,22 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         if ((rc = wait_snapshot(c, 0))) return rc;
         diffC = c->snap[0].s.diffC;
         diffM = c->snap[0].s.diffM;
+        if (c->pending_persist) {
+            // the persistent solve was not waited for on its own: this one record
+            // carries its iteration count next to the Picard residuals
+            const DevScal &fin = c->snap[0].s;
+            c->pending_persist = false;
+            if (fin.error) {
+                c->err = "peer exchange timed out (a rank stopped posting)";
+                return PDEODE_ERR_CUDA;
+            }
+            c->phase += 2ULL * (unsigned long long)fin.nit;   // two exchanges per iteration
+            c->ip = c->pending_ip0 ^ (int)(fin.nit & 1);
+            c->p = c->pbuf[c->ip];
+            nit = fin.nit;
+            stop = fin.stop;
+        }
+        if (stop == -1 || stop == -101) warn = PDEODE_WARN_CG_CAP;
 
         if (nit > mx) mx = nit;                      // P:722
         sum += nit;                                  // P:723
