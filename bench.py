@@ -185,7 +185,9 @@ def workload_config(args, nranks):
                     "(D(M), Picard loop, CG solves, C update)",
         "grid": [args.grid, args.grid],
         "parallelism": f"row-slabs x{nranks}" if nranks > 1 else "single GPU",
-        "l2": "inputs larger than L2: 12 fp64 fields of the grid stay resident "
+        "l2": ("inputs larger than L2: " if 12 * 8 * args.grid * args.grid > 4 * 126e6 else
+               "NOT larger than L2 (small --grid; no roofline claim): ") +
+              "12 fp64 fields of the grid stay resident "
               f"({12 * 8 * args.grid * args.grid / 1e6:.0f} MB total vs 126 MB L2); no flush",
     }
 

@@ -203,6 +203,8 @@ struct LaunchCfg {
     // p_nstrips * p_nchunks CTAs of p_BS consumer threads
     int persist, p_BS, p_nstrips, p_nchunks;
     int kb_reverse;        // K_B sweeps against K_A's direction
+    int i_BS, i_TR;        // launch shape of the INIT kernel (two IEEE divides per cell: it
+                           // wants more warps per SM than the SpMV does)
 };
 cudaError_t launch_cg_persist(const PersistArgs &a, int BS, cudaStream_t st);
 // Heuristic defaults for a grid, then PDEODE_BS / PDEODE_TR / PDEODE_DEPTH /

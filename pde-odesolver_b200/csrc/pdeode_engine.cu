@@ -229,6 +229,7 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     }
     StencilArgs a = stencil_args(c);
     a.x0 = x0; a.x = x; a.Cc = c->Cb[c->iC]; a.Mprev = c->Mb[c->iMprev];
+    a.BS = c->cfg.i_BS; a.TR = c->cfg.i_TR;
     a.post_phase = ++c->phase;
     CK(launch_stencil_init(a, c->stream));
     c->launches++;
@@ -501,7 +502,8 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
 
     c->cfg = launch_config(c->g);
     // the marching kernels never launch more CTAs than stencil_max_blocks(g, TR)
-    c->max_blocks = std::max(stencil_max_blocks(c->g, c->cfg.TR), std::max(stream_blocks(), 512));
+    c->max_blocks = std::max(stencil_max_blocks(c->g, std::min(c->cfg.TR, c->cfg.i_TR)),
+                             std::max(stream_blocks(), 512));
     CK(cudaMalloc(&c->partials, sizeof(double) * 8 * (size_t)c->max_blocks));
     {
         const size_t G = (size_t)std::max(1, c->cfg.p_nstrips * c->cfg.p_nchunks);
@@ -999,7 +1001,12 @@ int pdeode_time_kernel(pdeode_ctx *c, int kernel, int reps, float *ms_per_launch
         switch (kernel) {
         case PDEODE_KERNEL_CG_SPMV: CK(launch_stencil_cg(a, c->stream)); break;
         case PDEODE_KERNEL_CG_UPDATE: CK(launch_update(u, c->stream)); break;
-        case PDEODE_KERNEL_INIT: CK(launch_stencil_init(a, c->stream)); break;
+        case PDEODE_KERNEL_INIT: {
+            StencilArgs ai = a;
+            ai.BS = c->cfg.i_BS; ai.TR = c->cfg.i_TR;
+            CK(launch_stencil_init(ai, c->stream));
+            break;
+        }
         case PDEODE_KERNEL_SOLVEC: CK(launch_solvec(sc, c->stream)); break;
         case PDEODE_KERNEL_DIFFCOEF:
             CK(launch_diffcoef(c->g, c->np, c->Mb[c->iM], c->d, c->stream)); break;

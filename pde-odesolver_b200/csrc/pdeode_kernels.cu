@@ -739,6 +739,146 @@ __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- INIT, bulk-async staged
+
+// k_stencil<MODE_INIT>'s arithmetic behind the same shared-memory ring as
+// k_spmv_bulk: the ring's four lanes carry x0 (with halo), Mprev, d (with halo)
+// and C instead of r, p, d, ac.  The register-staged INIT reached 0.58 of the
+// measured HBM peak; this one streams like K_A.
+template <int BS, int DEPTH>
+__global__ void __launch_bounds__(BS + 32) k_init_bulk(const StencilArgs a) {
+    constexpr int TC = Ring<BS, DEPTH>::TC, SEG = Ring<BS, DEPTH>::SEG;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double sm[64];
+    Ring<BS, DEPTH> R;
+    R.carve(smem_raw);
+    DevScal *S = a.S;
+    const GridDesc g = a.g;
+    const NumParams np = a.np;
+    const int tid = threadIdx.x;
+    const int jt = blockIdx.x * TC;
+    const int i_begin = blockIdx.y * a.TR;
+    const int i_end = min(i_begin + a.TR, g.rows);
+    if (tid == 0) R.init_barriers();
+    __syncthreads();
+
+    double acc0 = 0.0, acc1 = 0.0;
+    if (tid >= BS) {
+        // lanes: s_r <- x0, s_p <- Mprev, s_d <- d, s_ac <- C (rows i_begin..i_end-1 only)
+        if (tid == BS)
+            bulk_produce<BS, DEPTH>(R, g, a.x0, a.Mprev, a.d, a.Cc, false, jt, i_begin, i_end, 0);
+    } else {
+        const int lane = tid & 31;
+        const int j0 = jt + 2 * tid;
+        const bool inrow = j0 < g.P;
+        const double h = np.h;
+        const bool firstc0 = (j0 == 0);
+        const bool lastc0 = (j0 == g.col - 1), lastc1 = (j0 + 1 == g.col - 1);
+        const bool valid0 = j0 < g.col, valid1 = j0 + 1 < g.col;
+        const int c0 = 2 * tid + 2;
+        const int ce = (lane == 0) ? c0 - 1 : c0 + 2;
+        double2 vN, vC, vS, dN, dC, dS, cC, cS, mC, mS;
+        double veC = 0.0, deC = 0.0, veS = 0.0, deS = 0.0;
+        vN = vC = vS = dN = dC = dS = cC = cS = mC = mS = make_double2(0.0, 0.0);
+        auto take = [&](long long kk, double2 &v, double2 &d, double2 &cc, double2 &mp, double &ve,
+                        double &de) {
+            const int s = (int)(kk % DEPTH);
+            mbar_wait(&R.full[s], (unsigned)(kk / DEPTH) & 1u);
+            const double *sx = R.s_r + s * SEG, *sd = R.s_d + s * SEG;
+            if (inrow) {
+                v = *reinterpret_cast<const double2 *>(sx + c0);
+                d = *reinterpret_cast<const double2 *>(sd + c0);
+                cc = *reinterpret_cast<const double2 *>(R.s_ac + s * TC + 2 * tid);
+                mp = *reinterpret_cast<const double2 *>(R.s_p + s * SEG + c0);
+                if (lane == 0 || lane == 31) { ve = sx[ce]; de = sd[ce]; }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&R.empty[s]);
+        };
+        double2 dm1, dm2;
+        double du1, du2;
+        take(0, vN, dN, dm1, dm2, du1, du2);
+        take(1, vC, dC, cC, mC, veC, deC);
+        long long off = (long long)i_begin * g.P + j0;
+        for (int i = i_begin; i < i_end; ++i, off += g.P) {
+            take((long long)(i - i_begin) + 2, vS, dS, cS, mS, veS, deS);
+            double vW0 = __shfl_up_sync(FULL, vC.y, 1);
+            double dW0 = __shfl_up_sync(FULL, dC.y, 1);
+            double vE1 = __shfl_down_sync(FULL, vC.x, 1);
+            double dE1 = __shfl_down_sync(FULL, dC.x, 1);
+            if (lane == 0) { vW0 = veC; dW0 = deC; }
+            if (lane == 31) { vE1 = veC; dE1 = deC; }
+            if (inrow) {
+                const int gi = g.row0 + i;
+                const bool first = (gi == 0);
+                const bool lastrow = (gi == g.grow - 1);
+                const bool quirkrow = (gi == g.grow - 2);
+                const double aN0 = h * (dN.x + dC.x), aN1 = h * (dN.y + dC.y);
+                const double aS0 = h * (dS.x + dC.x), aS1 = h * (dS.y + dC.y);
+                const double aW0 = h * (dW0 + dC.x);
+                const double aM = h * (dC.y + dC.x);
+                const double aE1 = h * (dE1 + dC.y);
+                double2 ac2, r2;
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    const bool firstc = c ? false : firstc0;
+                    const bool lastc = c ? lastc1 : lastc0;
+                    const bool lastq = lastrow || (quirkrow && lastc);
+                    const double aN = c ? aN1 : aN0, aS = c ? aS1 : aS0;
+                    const double aW = c ? aM : aW0, aE = c ? aE1 : aM;
+                    const double xN = c ? vN.y : vN.x, xS = c ? vS.y : vS.x;
+                    const double xC = c ? vC.y : vC.x;
+                    const double xW = c ? vC.x : vW0, xE = c ? vE1 : vC.y;
+                    const double A1 = first ? 0.0 : (lastq ? -(aN + aN) : -aN);
+                    const double A5 = lastq ? 0.0 : (first ? -(aS + aS) : -aS);
+                    const double A2 = firstc ? 0.0 : (lastc ? -(aW + aW) : -aW);
+                    const double A4 = lastc ? 0.0 : (firstc ? -(aE + aE) : -aE);
+                    // centre: blocks 1..4 in order, then - f + (1/tDel)  (P:554-585)
+                    const double t1 = first ? aS : aN;
+                    const double t2 = firstc ? aE : aW;
+                    const double t3 = lastc ? aW : aE;
+                    const double t4 = lastq ? aN : aS;
+                    const double mpc = c ? mC.y : mC.x;
+                    const double f = ffunc(mpc, c ? cC.y : cC.x, np);
+                    const double A3 = (((t1 + t2) + t3) + t4) - f + np.inv_dt;
+                    double y = A1 * xN;                                    // P:1093-1100
+                    y = y + A2 * xW;
+                    y = y + A3 * xC;
+                    y = y + A4 * xE;
+                    y = y + A5 * xS;
+                    const bool valid = c ? valid1 : valid0;
+                    const double rhs = mpc / np.tDel;                      // P:586
+                    const double rr = valid ? (rhs - y) : 0.0;             // CG:49
+                    if (c) { r2.y = rr; ac2.y = valid ? A3 : 0.0; } else { r2.x = rr; ac2.x = valid ? A3 : 0.0; }
+                    acc0 += rr * rr;
+                    acc1 += valid ? xC * xC : 0.0;
+                }
+                st2(a.ac + off, ac2);
+                st2(a.r + off, r2);
+                if (a.x != a.x0) st2(a.x + off, vC);
+                if (a.fuse_scalars == SUMS_PEER) {
+                    if (i == 0 && a.pc.r_up) st2(a.pc.r_up + (long long)a.pc.rows_up * g.P + j0, r2);
+                    if (i == g.rows - 1 && a.pc.r_dn) st2(a.pc.r_dn - g.P + j0, r2);
+                }
+            }
+            vN = vC; vC = vS; dN = dC; dC = dS; cC = cS; mC = mS; veC = veS; deC = deS;
+        }
+    }
+    const int nb = gridDim.x * gridDim.y;
+    const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm,
+                  a.fuse_scalars == SUMS_PEER)) {
+        if (a.fuse_scalars == SUMS_FUSED) {
+            scal_after_init(S, acc0, acc1);
+        } else if (a.fuse_scalars == SUMS_PEER) {
+            scal_after_init(S, 0.0, 0.0);
+            peer_post(a.pc, a.post_phase, acc0, acc1);
+        } else {
+            S->part[0] = acc0; S->part[1] = acc1;
+        }
+    }
+}
+
 // ---------------------------------------------------------------- CG vector update
 
 // sol += alfa p ; r -= alfa q (CG:79-82) and the two sums the next iteration
@@ -1374,6 +1514,9 @@ LaunchCfg launch_config(const GridDesc &g) {
     // measured at 4096^2 (bench.py): 6.29e10 with the reverse sweep and 16 CTAs per SM
     // against 5.95e10 forward with 8
     c.kb_reverse = 1;
+    // INIT (sweep at 4096^2): bulk BS 128 x 32 rows 0.200 ms, BS 256 x 64 rows 0.322 ms
+    c.i_BS = c.BS > 128 ? 128 : c.BS;
+    c.i_TR = c.TR > 32 ? 32 : c.TR;
     if (const char *e = getenv("PDEODE_KB_REVERSE")) c.kb_reverse = atoi(e) != 0;
     return c;
 }
@@ -1407,7 +1550,28 @@ static cudaError_t launch_stencil(const StencilArgs &a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
+template <int BS>
+static cudaError_t launch_init_bulk(const StencilArgs &a, cudaStream_t st) {
+    constexpr int DEPTH = 4;
+    constexpr size_t smem = Ring<BS, DEPTH>::BYTES;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(k_init_bulk<BS, DEPTH>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr_set = true;
+    }
+    dim3 grid(cdiv(a.g.P, 2 * BS), cdiv(a.g.rows, a.TR));
+    k_init_bulk<BS, DEPTH><<<grid, BS + 32, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_stencil_init(const StencilArgs &a, cudaStream_t st) {
+    if (a.variant == 1) {
+        if (a.BS == 64) return launch_init_bulk<64>(a, st);
+        if (a.BS == 128) return launch_init_bulk<128>(a, st);
+        return launch_init_bulk<256>(a, st);
+    }
     return launch_stencil<MODE_INIT>(a, st);
 }
 template <int BS, int DEPTH>
