@@ -16,33 +16,55 @@ namespace pdeode_host {
 // gfortran list-directed REAL(8): one separator blank, then G25.17E3 --
 // F20.(17-k) followed by five blanks when 0.1 <= |x| < 1e17 (k = digits before
 // the point), else 1PE25.16E3.
-std::string fmt_real(double x) {
-    char buf[64];
-    std::string body;
-    if (std::isnan(x)) body = "NaN";
-    else if (std::isinf(x)) body = x > 0 ? "Infinity" : "-Infinity";
-    if (!body.empty()) {
-        snprintf(buf, sizeof buf, " %25s", body.c_str());
-        return buf;
+// Writes the 26 characters of one list-directed REAL(8) item into out (no NUL).
+// One conversion per number: the 17 significant digits of "%.16E" are re-pointed
+// for the F form instead of being converted a second time.
+static void fmt_real_to(char *out, double x) {
+    memset(out, ' ', 26);
+    if (std::isnan(x)) { memcpy(out + 23, "NaN", 3); return; }
+    if (std::isinf(x)) {
+        if (x > 0) memcpy(out + 18, "Infinity", 8); else memcpy(out + 17, "-Infinity", 9);
+        return;
     }
-    if (x == 0.0) {
-        snprintf(buf, sizeof buf, " %20.16f     ", x);
-        return buf;
+    if (x == 0.0) {                               // F20.16 + 5 blanks
+        const bool neg = std::signbit(x);
+        memcpy(out + 3, "0.0000000000000000", 18);
+        if (neg) out[2] = '-';
+        return;
     }
     char e[40];
-    snprintf(e, sizeof e, "%.16E", x);          // d.ddddddddddddddddE+XX, rounded to 17 digits
-    const char *ep = strchr(e, 'E');
+    snprintf(e, sizeof e, "%.16E", x);            // [-]d.ddddddddddddddddE+XX, rounded to 17 digits
+    const bool neg = (e[0] == '-');
+    const char *m = e + (neg ? 1 : 0);            // d.dddd...
+    const char *ep = strchr(m, 'E');
     const int ex = atoi(ep + 1);
-    const int k = ex + 1;
+    const int k = ex + 1;                         // digits before the point in F form
+    char dig[17];
+    dig[0] = m[0];
+    memcpy(dig + 1, m + 2, 16);
     if (k >= 0 && k <= 17) {
-        snprintf(buf, sizeof buf, " %20.*f     ", 17 - k, x);
-        return buf;
+        // F20.(17-k) right-justified in 20 columns after the separator blank, then 5 blanks
+        char body[24];
+        int n = 0;
+        if (neg) body[n++] = '-';
+        if (k == 0) { body[n++] = '0'; body[n++] = '.'; memcpy(body + n, dig, 17); n += 17; }
+        else { memcpy(body + n, dig, k); n += k; body[n++] = '.'; memcpy(body + n, dig + k, 17 - k); n += 17 - k; }
+        memcpy(out + 1 + (20 - n), body, n);
+        return;
     }
-    std::string mant(e, ep - e);
-    char es[16];
-    snprintf(es, sizeof es, "E%c%03d", ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
-    snprintf(buf, sizeof buf, " %25s", (mant + es).c_str());
-    return buf;
+    // 1PE25.16E3
+    char body[28];
+    int n = 0;
+    if (neg) body[n++] = '-';
+    memcpy(body + n, m, 18); n += 18;             // d.dddddddddddddddd
+    n += snprintf(body + n, sizeof body - n, "E%c%03d", ex < 0 ? '-' : '+', ex < 0 ? -ex : ex);
+    memcpy(out + 1 + (25 - n), body, n);
+}
+
+std::string fmt_real(double x) {
+    char buf[26];
+    fmt_real_to(buf, x);
+    return std::string(buf, 26);
 }
 
 std::string fmt_int(long long v) {
@@ -324,10 +346,13 @@ void print_frame(FILE *f, const RunParams &p, int nro, int nco, const double *Md
     const int filter = frame_filter(p.row);
     for (int oi = 0; oi < nro; ++oi) {
         for (int oj = 0; oj < nco; ++oj) {
-            std::string s = fmt_real((double)(oj * filter) / (double)(p.col - 1)) +
-                            fmt_real((double)(oi * filter) / (double)(p.row - 1)) +
-                            fmt_real(Md[(size_t)oi * nco + oj]) + fmt_real(Cd[(size_t)oi * nco + oj]);
-            put(f, s);
+            char line[105];
+            fmt_real_to(line, (double)(oj * filter) / (double)(p.col - 1));
+            fmt_real_to(line + 26, (double)(oi * filter) / (double)(p.row - 1));
+            fmt_real_to(line + 52, Md[(size_t)oi * nco + oj]);
+            fmt_real_to(line + 78, Cd[(size_t)oi * nco + oj]);
+            line[104] = '\n';
+            fwrite(line, 1, 105, f);
         }
         put(f, "  ");
     }
