@@ -343,7 +343,12 @@ def main():
         s.step()
         peak, peak_src = measured_peak()
         ks = {}
-        for name, kid in (("cg_spmv", pb.KERNEL_CG_SPMV), ("cg_update", pb.KERNEL_CG_UPDATE)):
+        info = s.engine_info()
+        deferred = info.get("defer_x") == "1"
+        # 88-byte iteration: x += alfa p rides in the SpMV kernel, the update kernel does r only
+        kinds = ((("cg_spmv", pb.KERNEL_CG_SPMV_X), ("cg_update", pb.KERNEL_CG_UPDATE_R)) if deferred
+                 else (("cg_spmv", pb.KERNEL_CG_SPMV), ("cg_update", pb.KERNEL_CG_UPDATE)))
+        for name, kid in kinds:
             ms = s.time_kernel(kid, args.kernel_reps)
             by = pb.Solver.bytes_per_cell(kid) * n
             ks[name] = {"ms": ms, "GBps": by / ms / 1e6, "bytes_per_cell": pb.Solver.bytes_per_cell(kid)}
@@ -358,9 +363,10 @@ def main():
                 traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["GBps"], "peak": peak,
                 "unit": "GB/s", "frac": ks[dom]["GBps"] / peak, "traffic": traffic,
-                "peak_source": peak_src, "kernels": ks,
+                "peak_source": peak_src, "kernels": ks, "engine": info,
                 "cg_iteration": {
                     "bytes_per_cell": 96,
+                    "bytes_per_cell_moved": sum(k["bytes_per_cell"] for k in ks.values()),
                     "ms": ks["cg_spmv"]["ms"] + ks["cg_update"]["ms"],
                     "GBps": 96 * n / (ks["cg_spmv"]["ms"] + ks["cg_update"]["ms"]) / 1e6,
                     "frac": 96 * n / (ks["cg_spmv"]["ms"] + ks["cg_update"]["ms"]) / 1e6 / peak}}

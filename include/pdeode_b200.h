@@ -174,6 +174,10 @@ int pdeode_debug_get_array(pdeode_ctx *ctx, int which, double *out);
  * 2 = inside the CG kernels over NVLink peer memory (CUDA-IPC mappings). */
 int pdeode_exchange_mode(const pdeode_ctx *ctx, int *mode);
 
+/* One line describing the engine this context chose: SpMV variant, launch
+ * shapes, persistent solve, 88-byte iteration, exchange. */
+int pdeode_engine_info(const pdeode_ctx *ctx, char *buf, int len);
+
 /* Kernels launched by this context so far. */
 int pdeode_launch_count(const pdeode_ctx *ctx, long long *launches);
 
@@ -186,6 +190,8 @@ int pdeode_launch_count(const pdeode_ctx *ctx, long long *launches);
 #define PDEODE_KERNEL_INIT       2  /* centre diagonal + r = b - A x0 */
 #define PDEODE_KERNEL_SOLVEC     3  /* C update + Picard residuals */
 #define PDEODE_KERNEL_DIFFCOEF   4  /* D(M) */
+#define PDEODE_KERNEL_CG_SPMV_X  5  /* CG_SPMV + the previous iteration's x += alfa p; x.x (88-byte iteration) */
+#define PDEODE_KERNEL_CG_UPDATE_R 6 /* r -= alfa q; r.r (88-byte iteration) */
 int pdeode_time_kernel(pdeode_ctx *ctx, int kernel, int reps,
                        float *ms_per_launch);
 

@@ -113,6 +113,8 @@ struct StencilArgs {
     int BS;                // consumer threads per CTA (64 | 128 | 256); strip = 2*BS columns
     int DEPTH;             // ring depth in rows of the bulk-async variant
     int variant;           // CG SpMV: 0 register-staged, 1 bulk-async staged (default)
+    int defer_x;           // 1: the SpMV kernel also applies the previous iteration's x += alfa p
+                           // (x = StencilArgs::x) and sums x.x; the update kernel then only does r
     int fuse_scalars;      // SUMS_RAW | SUMS_FUSED | SUMS_PEER
     int write_ghost_top, write_ghost_bot; // maintain p ghost rows (multi rank)
     long long seq;
@@ -141,6 +143,7 @@ struct UpdateArgs {
     long long n2;          // number of double2 elements to stream (rows*P/2)
     int fuse_scalars;
     int reverse;           // 1: sweep high -> low addresses (L2 reuse against the SpMV kernel)
+    int r_only;            // 1: x is updated by the next SpMV kernel (88-byte iteration)
     long long seq;
     NumParams np;          // SUMS_PEER: the stop test runs in this kernel's last CTA
     double *trace;
@@ -175,6 +178,9 @@ cudaError_t launch_diffcoef(const GridDesc &g, const NumParams &np, const double
 cudaError_t launch_stencil_init(const StencilArgs &a, cudaStream_t st);
 cudaError_t launch_stencil_cg(const StencilArgs &a, cudaStream_t st);
 cudaError_t launch_update(const UpdateArgs &a, cudaStream_t st);
+cudaError_t launch_update_r(const UpdateArgs &a, cudaStream_t st);
+cudaError_t launch_xtail(double *x, const double *p, const DevScal *S, long long n2,
+                         cudaStream_t st);
 cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st);
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t st);
 cudaError_t launch_init_cond(const GridDesc &g, int ic, double depth, double height, double xDel,
@@ -203,6 +209,7 @@ struct LaunchCfg {
     // p_nstrips * p_nchunks CTAs of p_BS consumer threads
     int persist, p_BS, p_nstrips, p_nchunks;
     int kb_reverse;        // K_B sweeps against K_A's direction
+    int defer_x;           // 88-byte iteration: x += alfa p deferred into the next SpMV kernel
     int i_BS, i_TR;        // launch shape of the INIT kernel (two IEEE divides per cell: it
                            // wants more warps per SM than the SpMV does)
 };

@@ -124,6 +124,11 @@ int fail_nccl(pdeode_ctx *c, int e, const char *what) {
     } while (0)
 
 inline bool multi(const pdeode_ctx *c) { return c->nranks > 1; }
+inline int sums_mode(const pdeode_ctx *c);
+// 88-byte iteration: single rank, bulk-async SpMV, kernel-per-phase engine only
+inline bool defer_x(const pdeode_ctx *c) {
+    return c->cfg.defer_x && c->nranks == 1 && c->cfg.variant == 1 && !c->cfg.persist;
+}
 inline int sums_mode(const pdeode_ctx *c) {
     return !multi(c) ? SUMS_FUSED : (c->peer ? SUMS_PEER : SUMS_RAW);
 }
@@ -183,9 +188,12 @@ StencilArgs stencil_args(pdeode_ctx *c) {
 // one CG iteration: CG:55-90
 int cg_iteration(pdeode_ctx *c, double *x) {
     const int mode = sums_mode(c);
+    const bool defer = defer_x(c);
     StencilArgs a = stencil_args(c);
     a.wait_phase = c->phase;                 // posted by INIT or the previous K_B
     a.post_phase = ++c->phase;
+    a.defer_x = defer ? 1 : 0;
+    a.x = x;
     CK(launch_stencil_cg(a, c->stream));
     c->launches++;
     c->ip ^= 1;                      // the direction just written is the current one
@@ -206,7 +214,8 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     u.np = c->np; u.trace = a.trace; u.pc = c->pc;
     u.wait_phase = c->phase;                 // posted by the K_A just launched
     u.post_phase = ++c->phase;
-    CK(launch_update(u, c->stream));
+    if (defer) CK(launch_update_r(u, c->stream));    // 88-byte iteration: r only
+    else CK(launch_update(u, c->stream));
     c->launches++;
     if (mode == SUMS_RAW) {
         int rc = allreduce_part(c, 2);
@@ -312,6 +321,11 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     // iteration sits in the buffer given by the parity of nit
     c->ip = ip0 ^ (int)(fin.nit & 1);
     c->p = c->pbuf[c->ip];
+    if (defer_x(c)) {
+        // the x update of the last iteration was deferred to a kernel that never ran
+        CK(launch_xtail(x, c->p, c->S, (long long)c->g.rows * c->g.P / 2, c->stream));
+        c->launches++;
+    }
     *nit_out = fin.nit;
     *stop_out = fin.stop;
     c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)] = (int)std::min<long long>(fin.nit, 1 << 20);
@@ -952,6 +966,18 @@ int pdeode_exchange_mode(const pdeode_ctx *c, int *mode) {
     return PDEODE_OK;
 }
 
+int pdeode_engine_info(const pdeode_ctx *c, char *buf, int len) {
+    if (!c || !buf || len < 1) return PDEODE_ERR_ARG;
+    snprintf(buf, (size_t)len,
+             "spmv=%s BS=%d TR=%d depth=%d init_BS=%d init_TR=%d persist=%d persist_ctas=%d "
+             "defer_x=%d kb_reverse=%d exchange=%s",
+             c->cfg.variant == 1 ? "bulk-async" : "register-staged", c->cfg.BS, c->cfg.TR,
+             c->cfg.DEPTH, c->cfg.i_BS, c->cfg.i_TR, c->cfg.persist,
+             c->cfg.p_nstrips * c->cfg.p_nchunks, defer_x(c) ? 1 : 0, c->cfg.kb_reverse,
+             !multi(c) ? "none" : (c->peer ? "peer" : "nccl"));
+    return PDEODE_OK;
+}
+
 int pdeode_launch_count(const pdeode_ctx *c, long long *launches) {
     if (!c || !launches) return PDEODE_ERR_ARG;
     *launches = c->launches;
@@ -965,6 +991,8 @@ int pdeode_kernel_bytes_per_cell(int kernel) {
     case PDEODE_KERNEL_INIT: return 56;       // R x0,d,C,Mprev  W ac,r,x
     case PDEODE_KERNEL_SOLVEC: return 48;     // R Mprev,Mnew,Cprev,C,M  W Cnew
     case PDEODE_KERNEL_DIFFCOEF: return 16;   // R Mprev  W d
+    case PDEODE_KERNEL_CG_SPMV_X: return 64;  // R r,p,d,ac,x  W p,q,x
+    case PDEODE_KERNEL_CG_UPDATE_R: return 24;  // R r,q  W r
     default: return 0;
     }
 }
@@ -1001,6 +1029,13 @@ int pdeode_time_kernel(pdeode_ctx *c, int kernel, int reps, float *ms_per_launch
         switch (kernel) {
         case PDEODE_KERNEL_CG_SPMV: CK(launch_stencil_cg(a, c->stream)); break;
         case PDEODE_KERNEL_CG_UPDATE: CK(launch_update(u, c->stream)); break;
+        case PDEODE_KERNEL_CG_SPMV_X: {
+            StencilArgs ax = a;
+            ax.defer_x = 1; ax.x = u.x; ax.variant = 1;
+            CK(launch_stencil_cg(ax, c->stream));
+            break;
+        }
+        case PDEODE_KERNEL_CG_UPDATE_R: CK(launch_update_r(u, c->stream)); break;
         case PDEODE_KERNEL_INIT: {
             StencilArgs ai = a;
             ai.BS = c->cfg.i_BS; ai.TR = c->cfg.i_TR;

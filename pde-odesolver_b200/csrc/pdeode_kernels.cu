@@ -128,6 +128,39 @@ __device__ __forceinline__ bool grid_sum2(double &a, double &b, double *partials
     return threadIdx.x == 0;
 }
 
+// Same for a triple (partials: [3][nb]).
+__device__ __forceinline__ bool grid_sum3(double &a, double &b, double &c, double *partials,
+                                          int nb, int bid, unsigned int *ticket, double *sm,
+                                          bool sysfence = false) {
+    __shared__ int s_last3;
+    if (sysfence) __threadfence_system();
+    double z0 = 0.0;
+    block_sum2(a, b, sm);
+    block_sum2(c, z0, sm);
+    if (threadIdx.x == 0) {
+        partials[bid] = a;
+        partials[nb + bid] = b;
+        partials[2 * nb + bid] = c;
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_last3 = (t == (unsigned int)(nb - 1));
+    }
+    __syncthreads();
+    if (!s_last3) return false;
+    __threadfence();
+    double x = 0.0, y = 0.0, z = 0.0, z1 = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+        x += __ldcg(partials + i);
+        y += __ldcg(partials + nb + i);
+        z += __ldcg(partials + 2 * nb + i);
+    }
+    block_sum2(x, y, sm);
+    block_sum2(z, z1, sm);
+    a = x; b = y; c = z;
+    if (threadIdx.x == 0) *ticket = 0u;
+    return threadIdx.x == 0;
+}
+
 // ---------------------------------------------------------------- scalars
 
 // CG:53 (nit = 0, stopcrit = 0) with rho / sum(sol*sol) of the start vector
@@ -530,15 +563,16 @@ template <int BS, int DEPTH>
 struct Ring {
     static constexpr int TC = 2 * BS;          // columns per strip
     static constexpr int SEG = TC + 4;         // doubles per staged row segment (halo 2 + 2)
-    static constexpr size_t BYTES = (size_t)DEPTH * (3 * SEG + TC) * sizeof(double) + 2 * DEPTH * 8;
-    double *s_r, *s_p, *s_d, *s_ac;
+    static constexpr size_t BYTES = (size_t)DEPTH * (3 * SEG + 2 * TC) * sizeof(double) + 2 * DEPTH * 8;
+    double *s_r, *s_p, *s_d, *s_ac, *s_x;
     unsigned long long *full, *empty;
     __device__ __forceinline__ void carve(unsigned char *raw) {
         s_r = reinterpret_cast<double *>(raw);                     // [DEPTH][SEG]
         s_p = s_r + DEPTH * SEG;                                   // [DEPTH][SEG]
         s_d = s_p + DEPTH * SEG;                                   // [DEPTH][SEG]
         s_ac = s_d + DEPTH * SEG;                                  // [DEPTH][TC]
-        full = reinterpret_cast<unsigned long long *>(s_ac + DEPTH * TC);
+        s_x = s_ac + DEPTH * TC;                                   // [DEPTH][TC] (88-byte iteration)
+        full = reinterpret_cast<unsigned long long *>(s_x + DEPTH * TC);
         empty = full + DEPTH;
     }
     __device__ __forceinline__ void init_barriers() {
@@ -555,7 +589,8 @@ template <int BS, int DEPTH>
 __device__ __forceinline__ void bulk_produce(const Ring<BS, DEPTH> &R, const GridDesc &g,
                                              const double *r, const double *p_in,
                                              const double *d, const double *ac, bool firstit,
-                                             int jt, int i_begin, int i_end, long long K) {
+                                             int jt, int i_begin, int i_end, long long K,
+                                             const double *xsrc = nullptr) {
     constexpr int TC = Ring<BS, DEPTH>::TC, SEG = Ring<BS, DEPTH>::SEG;
     const int nstage = (i_end - i_begin) + 2;
     // segment [jt-2, jt-2+seglen): never past 2 doubles beyond the row (guard)
@@ -567,12 +602,15 @@ __device__ __forceinline__ void bulk_produce(const Ring<BS, DEPTH> &R, const Gri
         const int i = i_begin - 1 + k;
         const long long off = (long long)i * g.P + (jt - 2);
         const bool has_ac = (k >= 1 && k <= nstage - 2);
-        const unsigned tx = segbytes * (firstit ? 2u : 3u) + (has_ac ? acbytes : 0u);
+        const bool has_x = has_ac && xsrc != nullptr;
+        const unsigned tx = segbytes * (firstit ? 2u : 3u) + (has_ac ? acbytes : 0u) +
+                            (has_x ? acbytes : 0u);
         mbar_expect_tx(&R.full[s], tx);
         bulk_g2s(R.s_r + s * SEG, r + off, segbytes, &R.full[s]);
         if (!firstit) bulk_g2s(R.s_p + s * SEG, p_in + off, segbytes, &R.full[s]);
         bulk_g2s(R.s_d + s * SEG, d + off, segbytes, &R.full[s]);
         if (has_ac) bulk_g2s(R.s_ac + s * TC, ac + off + 2, acbytes, &R.full[s]);
+        if (has_x) bulk_g2s(R.s_x + s * TC, xsrc + off + 2, acbytes, &R.full[s]);
     }
 }
 
@@ -583,7 +621,9 @@ __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const Gri
                                              double h, double *p_out, double *q_out,
                                              bool firstit, double beta, int jt, int i_begin,
                                              int i_end, long long K, bool ghost_top,
-                                             bool ghost_bot, double &acc0, double &acc1) {
+                                             bool ghost_bot, double &acc0, double &acc1,
+                                             double *xdef = nullptr, double alfa_prev = 0.0,
+                                             double *acc2 = nullptr) {
     constexpr int TC = Ring<BS, DEPTH>::TC, SEG = Ring<BS, DEPTH>::SEG;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
@@ -600,7 +640,13 @@ __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const Gri
     vN = vC = vS = dN = dC = dS = acC = acS = make_double2(0.0, 0.0);
 
     // fetch one staged row into (v, d, ac, ve, de)
-    auto take = [&](long long kk, double2 &v, double2 &d, double2 &ac, double &ve, double &de) {
+    // deferred update (the 88-byte iteration): x += alfa_prev * p_prev rides along here,
+    // on the cells this thread owns, using the p_prev it reads anyway
+    const bool defer = (xdef != nullptr) && !firstit;
+    double2 pC = make_double2(0.0, 0.0), pS = pC, pdum = pC;
+    double2 xC = make_double2(0.0, 0.0), xS = xC, xdum = xC;
+    auto take = [&](long long kk, double2 &v, double2 &d, double2 &ac, double &ve, double &de,
+                    double2 &pv, double2 &xv) {
         const int s = (int)(kk % DEPTH);
         mbar_wait(&R.full[s], (unsigned)(kk / DEPTH) & 1u);
         const double *sr = R.s_r + s * SEG, *sp = R.s_p + s * SEG, *sd = R.s_d + s * SEG;
@@ -608,12 +654,14 @@ __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const Gri
             const double2 r2 = *reinterpret_cast<const double2 *>(sr + c0);
             d = *reinterpret_cast<const double2 *>(sd + c0);
             ac = *reinterpret_cast<const double2 *>(R.s_ac + s * TC + 2 * tid);
+            if (defer) xv = *reinterpret_cast<const double2 *>(R.s_x + s * TC + 2 * tid);
             if (firstit) {
                 v = r2;                                            // CG:64
             } else {
                 const double2 p2 = *reinterpret_cast<const double2 *>(sp + c0);
                 v.x = r2.x + beta * p2.x;                          // CG:71
                 v.y = r2.y + beta * p2.y;
+                pv = p2;
             }
             if (lane == 0 || lane == 31) {
                 ve = firstit ? sr[ce] : sr[ce] + beta * sp[ce];
@@ -626,13 +674,14 @@ __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const Gri
 
     double2 dummy;
     double dum1, dum2;
-    take(K, vN, dN, dummy, dum1, dum2);
-    take(K + 1, vC, dC, acC, veC, deC);
+    take(K, vN, dN, dummy, dum1, dum2, pdum, xdum);
+    take(K + 1, vC, dC, acC, veC, deC, pC, xC);
     long long off = (long long)i_begin * g.P + j0;
     if (ghost_top && i_begin == 0 && inrow) st2(p_out + off - g.P, vN);
 
     for (int i = i_begin; i < i_end; ++i, off += g.P) {
-        take(K + (i - i_begin) + 2, vS, dS, acS, veS, deS);
+        take(K + (i - i_begin) + 2, vS, dS, acS, veS, deS, pS, xS);
+        double2 x2 = xC;
         double vW0 = __shfl_up_sync(FULL, vC.y, 1);
         double dW0 = __shfl_up_sync(FULL, dC.y, 1);
         double vE1 = __shfl_down_sync(FULL, vC.x, 1);
@@ -678,8 +727,15 @@ __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const Gri
             }
             st2(p_out + off, vC);
             st2(q_out + off, q2);
+            if (defer) {
+                x2.x = x2.x + alfa_prev * pC.x;                    // CG:80 of the previous iteration
+                x2.y = x2.y + alfa_prev * pC.y;
+                st2(xdef + off, x2);
+                *acc2 += x2.x * x2.x;                              // CG:57 of this iteration
+                *acc2 += x2.y * x2.y;
+            }
         }
-        vN = vC; vC = vS; dN = dC; dC = dS; acC = acS; veC = veS; deC = deS;
+        vN = vC; vC = vS; dN = dC; dC = dS; acC = acS; veC = veS; deC = deS; pC = pS; xC = xS;
     }
     if (ghost_bot && i_end == g.rows && inrow) st2(p_out + off, vC);
 }
@@ -713,17 +769,33 @@ __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
     if (tid == 0) R.init_barriers();
     __syncthreads();
 
-    double acc0 = 0.0, acc1 = 0.0;
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
+    const double alfa_prev = S->alfa;               // of the previous iteration (deferred x update)
     if (tid >= BS) {
         if (tid == BS)
-            bulk_produce<BS, DEPTH>(R, g, a.r, a.p_in, a.d, a.ac, firstit, jt, i_begin, i_end, 0);
+            bulk_produce<BS, DEPTH>(R, g, a.r, a.p_in, a.d, a.ac, firstit, jt, i_begin, i_end, 0,
+                                    (a.defer_x && !firstit) ? a.x : nullptr);
     } else {
         bulk_consume<BS, DEPTH>(R, g, a.np.h, a.p, a.q, firstit, beta, jt, i_begin, i_end, 0,
-                                a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1);
+                                a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1,
+                                a.defer_x ? a.x : nullptr, alfa_prev, &acc2);
     }
 
     const int nb = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
+    if (a.defer_x) {
+        // 88-byte iteration (single rank): sum(sol*sol) of the iterate this kernel has just
+        // completed comes out of the same pass as p.q and p.p
+        if (grid_sum3(acc0, acc1, acc2, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm)) {
+            if (a.fuse_scalars == SUMS_FUSED) {
+                if (!firstit) S->xx = acc2;                          // CG:57
+                scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace, a.hs);
+            } else {
+                S->part[0] = acc0; S->part[1] = acc1; S->part[2] = acc2;
+            }
+        }
+        return;
+    }
     if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm,
                   a.fuse_scalars == SUMS_PEER)) {
         if (a.fuse_scalars == SUMS_FUSED) {
@@ -946,6 +1018,56 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         } else {
             S->part[0] = rr; S->part[1] = xx;
         }
+    }
+}
+
+// The update kernel of the 88-byte iteration: r -= alfa q and dotProd(r,r) only
+// (CG:81, CG:59); sol += alfa p (CG:80) is applied by the next SpMV kernel, which
+// reads p anyway, and by k_xtail after the last iteration.
+__global__ void __launch_bounds__(256) k_update_r(const UpdateArgs a) {
+    __shared__ double sm[64];
+    DevScal *S = a.S;
+    if (S->finished) return;
+    const double alfa = S->alfa;
+    const bool rev = a.reverse != 0;
+    double rr = 0.0, zz = 0.0;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + stride < a.n2; i += 2 * stride) {
+        const long long k0 = 2 * (rev ? a.n2 - 1 - i : i);
+        const long long k1 = 2 * (rev ? a.n2 - 1 - (i + stride) : i + stride);
+        double2 r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
+        double2 r1 = ld2(a.r + k1), q1 = ld2(a.q + k1);
+        r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
+        r1.x = r1.x - alfa * q1.x; r1.y = r1.y - alfa * q1.y;
+        st2(a.r + k0, r0); st2(a.r + k1, r1);
+        rr += r0.x * r0.x; rr += r0.y * r0.y; rr += r1.x * r1.x; rr += r1.y * r1.y;
+    }
+    for (; i < a.n2; i += stride) {
+        const long long k0 = 2 * (rev ? a.n2 - 1 - i : i);
+        double2 r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
+        r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
+        st2(a.r + k0, r0);
+        rr += r0.x * r0.x; rr += r0.y * r0.y;
+    }
+    if (grid_sum2(rr, zz, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_UPDATE], sm)) {
+        if (a.fuse_scalars == SUMS_FUSED)
+            scal_after_update(S, rr, S->xx, a.hs, a.seq);  // sum(sol*sol) is the SpMV kernel's now
+        else
+            S->part[0] = rr;
+    }
+}
+
+// sol += alfa p of the last iteration (CG:80), once per solve.
+__global__ void __launch_bounds__(256) k_xtail(double *__restrict__ x, const double *__restrict__ p,
+                                               const DevScal *S, long long n2) {
+    const double alfa = S->alfa;
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+        double2 x2 = ld2(x + 2 * i);
+        const double2 p2 = ld2(p + 2 * i);
+        x2.x = x2.x + alfa * p2.x; x2.y = x2.y + alfa * p2.y;
+        st2(x + 2 * i, x2);
     }
 }
 
@@ -1514,6 +1636,9 @@ LaunchCfg launch_config(const GridDesc &g) {
     // measured at 4096^2 (bench.py): 6.29e10 with the reverse sweep and 16 CTAs per SM
     // against 5.95e10 forward with 8
     c.kb_reverse = 1;
+    // 88-byte iteration (one GPU, kernel-per-phase engine): 6.53e10 against 6.2e10 at 4096^2
+    c.defer_x = 1;
+    if (const char *e = getenv("PDEODE_DEFER_X")) c.defer_x = atoi(e) != 0;
     // INIT (sweep at 4096^2): bulk BS 128 x 32 rows 0.200 ms, BS 256 x 64 rows 0.322 ms
     c.i_BS = c.BS > 128 ? 128 : c.BS;
     c.i_TR = c.TR > 32 ? 32 : c.TR;
@@ -1612,6 +1737,17 @@ cudaError_t launch_stencil_cg(const StencilArgs &a, cudaStream_t st) {
 
 cudaError_t launch_update(const UpdateArgs &a, cudaStream_t st) {
     k_update<<<flat_blocks((a.n2 + 1) / 2), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_update_r(const UpdateArgs &a, cudaStream_t st) {
+    k_update_r<<<flat_blocks((a.n2 + 1) / 2), 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_xtail(double *x, const double *p, const DevScal *S, long long n2,
+                         cudaStream_t st) {
+    k_xtail<<<flat_blocks(n2), 256, 0, st>>>(x, p, S, n2);
     return cudaGetLastError();
 }
 

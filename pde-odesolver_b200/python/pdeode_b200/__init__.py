@@ -23,6 +23,7 @@ NCCL_ID_BYTES = 128
 
 ARR_M, ARR_C, ARR_MNEW, ARR_D, ARR_AC, ARR_R, ARR_P, ARR_Q = range(8)
 KERNEL_CG_SPMV, KERNEL_CG_UPDATE, KERNEL_INIT, KERNEL_SOLVEC, KERNEL_DIFFCOEF = range(5)
+KERNEL_CG_SPMV_X, KERNEL_CG_UPDATE_R = 5, 6
 
 
 class Params(C.Structure):
@@ -91,6 +92,7 @@ def _lib():
         "pdeode_debug_get_array": [vp, C.c_int, vp],
         "pdeode_launch_count": [vp, llp],
         "pdeode_exchange_mode": [vp, ip],
+        "pdeode_engine_info": [vp, C.c_char_p, C.c_int],
         "pdeode_time_kernel": [vp, C.c_int, C.c_int, C.POINTER(C.c_float)],
         "pdeode_kernel_bytes_per_cell": [C.c_int],
     }
@@ -263,6 +265,11 @@ class Solver:
         v = C.c_int()
         self._ck(self.lib.pdeode_exchange_mode(self.h, C.byref(v)), "exchange_mode")
         return {0: "single", 1: "nccl", 2: "peer"}[v.value]
+
+    def engine_info(self):
+        buf = C.create_string_buffer(512)
+        self._ck(self.lib.pdeode_engine_info(self.h, buf, 512), "engine_info")
+        return dict(kv.split("=", 1) for kv in buf.value.decode().split())
 
     def launch_count(self):
         v = C.c_longlong()

@@ -33,10 +33,13 @@ def pb():
 def engine_env(monkeypatch):
     """Selects the CG engine of contexts created afterwards (read at pdeode_create)."""
     def select(engine):
-        for k in ("PDEODE_PERSIST", "PDEODE_VARIANT"):
+        for k in ("PDEODE_PERSIST", "PDEODE_VARIANT", "PDEODE_DEFER_X"):
             monkeypatch.delenv(k, raising=False)
-        if engine == "kernels":
+        if engine == "kernels":                      # kernel per phase, 88-byte iteration
             monkeypatch.setenv("PDEODE_PERSIST", "0")
+        elif engine == "kernels-96":                 # kernel per phase, x updated by K_B
+            monkeypatch.setenv("PDEODE_PERSIST", "0")
+            monkeypatch.setenv("PDEODE_DEFER_X", "0")
         elif engine == "persistent":
             monkeypatch.setenv("PDEODE_PERSIST", "1")
         elif engine == "register-staged":
@@ -202,7 +205,7 @@ def test_first_cg_iteration_scalars(pb):
     (64, 64, dict(dSelect=1, fSelect=5, tDel=1e-2), ("blobs", 0.3, 0.3, 4, 2), 3),
     (257, 257, {}, ("blobs", 0.02, 0.0390625, 60, 7), 4),     # shipped parameter.txt values
 ])
-@pytest.mark.parametrize("engine", ["kernels", "persistent", "register-staged"])
+@pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent", "register-staged"])
 def test_steps_match_oracle(pb, engine_env, row, col, over, ic, steps, engine):
     """Both CG engines -- one kernel per phase and the persistent cooperative
     solve -- and the register-staged SpMV variant, against the oracle."""
@@ -236,7 +239,7 @@ def test_1024_grid_matches_oracle(pb):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("engine", ["kernels", "persistent"])
+@pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent"])
 def test_golden_fixtures(pb, engine_env, name, engine):
     engine_env(engine)
     z, row, col, over = load_case(name)
