@@ -358,7 +358,7 @@ def main():
         if os.path.exists(tp):
             try:
                 with open(tp) as f:
-                    traffic = json.load(f).get(dom)
+                    traffic = json.load(f).get(dom + ({"cg_spmv": "_x", "cg_update": "_r"}[dom] if deferred else ""))
             except Exception:
                 traffic = None
         roof = {"bound": "hbm", "kernel": dom, "achieved": ks[dom]["GBps"], "peak": peak,

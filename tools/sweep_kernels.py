@@ -36,6 +36,7 @@ def main():
     n = row * col
     M0, C0 = ic1(row, col, 0.9, 0.3)
     kid = {"cg_spmv": pb.KERNEL_CG_SPMV, "cg_update": pb.KERNEL_CG_UPDATE,
+           "cg_spmv_x": pb.KERNEL_CG_SPMV_X, "cg_update_r": pb.KERNEL_CG_UPDATE_R,
            "init": pb.KERNEL_INIT, "solvec": pb.KERNEL_SOLVEC, "diffcoef": pb.KERNEL_DIFFCOEF}
     variants = args.variant.split(",") if args.variant else [""]
     for var in variants:
