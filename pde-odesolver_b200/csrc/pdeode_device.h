@@ -72,9 +72,10 @@ enum {
 
 constexpr int PEER_MAX_RANKS = 8;
 constexpr int PEER_SLOTS = 4;    // phases in flight never span more than two slots
+constexpr int PEER_VALS = 4;     // doubles per (slot, rank): up to three sums + pad
 
 // Peer-memory exchange of one context (multi rank).  Every rank owns a comm
-// block {slots[PEER_SLOTS][PEER_MAX_RANKS][2], flags[PEER_SLOTS][PEER_MAX_RANKS]}
+// block {slots[PEER_SLOTS][PEER_MAX_RANKS][PEER_VALS], flags[PEER_SLOTS][PEER_MAX_RANKS]}
 // that the other ranks write into through CUDA-IPC mappings; r_up / r_dn are the
 // neighbours' residual arrays, whose ghost rows this rank fills directly.
 struct PeerComm {

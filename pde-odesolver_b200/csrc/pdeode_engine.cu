@@ -125,9 +125,9 @@ int fail_nccl(pdeode_ctx *c, int e, const char *what) {
 
 inline bool multi(const pdeode_ctx *c) { return c->nranks > 1; }
 inline int sums_mode(const pdeode_ctx *c);
-// 88-byte iteration: single rank, bulk-async SpMV, kernel-per-phase engine only
+// 88-byte iteration: bulk-async SpMV, kernel-per-phase engine, one rank or peer exchange
 inline bool defer_x(const pdeode_ctx *c) {
-    return c->cfg.defer_x && c->nranks == 1 && c->cfg.variant == 1 && !c->cfg.persist;
+    return c->cfg.defer_x && (c->nranks == 1 || c->peer) && c->cfg.variant == 1 && !c->cfg.persist;
 }
 inline int sums_mode(const pdeode_ctx *c) {
     return !multi(c) ? SUMS_FUSED : (c->peer ? SUMS_PEER : SUMS_RAW);
@@ -214,7 +214,8 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     u.np = c->np; u.trace = a.trace; u.pc = c->pc;
     u.wait_phase = c->phase;                 // posted by the K_A just launched
     u.post_phase = ++c->phase;
-    if (defer) CK(launch_update_r(u, c->stream));    // 88-byte iteration: r only
+    u.r_only = defer ? 1 : 0;                        // 88-byte iteration: r only
+    if (defer && mode == SUMS_FUSED) CK(launch_update_r(u, c->stream));
     else CK(launch_update(u, c->stream));
     c->launches++;
     if (mode == SUMS_RAW) {
@@ -410,7 +411,7 @@ int setup_peer(pdeode_ctx *c) {
         int rows, ok;
     };
     const int nr = c->nranks;
-    const size_t slots_bytes = sizeof(double) * PEER_SLOTS * PEER_MAX_RANKS * 2;
+    const size_t slots_bytes = sizeof(double) * PEER_SLOTS * PEER_MAX_RANKS * PEER_VALS;
     const size_t flags_bytes = sizeof(unsigned long long) * PEER_SLOTS * PEER_MAX_RANKS;
     CK(cudaMalloc(&c->comm_block, slots_bytes + flags_bytes));
     CK(cudaMemset(c->comm_block, 0, slots_bytes + flags_bytes));

@@ -258,12 +258,13 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
 // A peer that never posts (crashed) makes the wait give up after ~1 s of GPU
 // clocks and raise DevScal::error instead of hanging the device.
 __device__ __forceinline__ void peer_wait_sums(const PeerComm &pc, unsigned long long phase,
-                                               DevScal *S, double &s0, double &s1) {
-    __shared__ double sh[2];
+                                               DevScal *S, double &s0, double &s1,
+                                               double *s2 = nullptr) {
+    __shared__ double sh[3];
     if (threadIdx.x == 0) {
         const int slot = (int)(phase % PEER_SLOTS);
         const unsigned long long *f = pc.flags + slot * PEER_MAX_RANKS;
-        const double *v = pc.slots + (size_t)slot * PEER_MAX_RANKS * 2;
+        const double *v = pc.slots + (size_t)slot * PEER_MAX_RANKS * PEER_VALS;
         const long long t0 = clock64();
         bool ok = true;
         for (int r = 0; r < pc.nranks && ok; ++r) {
@@ -271,16 +272,18 @@ __device__ __forceinline__ void peer_wait_sums(const PeerComm &pc, unsigned long
                 if (clock64() - t0 > 2000000000LL) { ok = false; break; }
             }
         }
-        double a = 0.0, b = 0.0;
+        double a = 0.0, b = 0.0, c = 0.0;
         for (int r = 0; r < pc.nranks; ++r) {
-            a += ld_relaxed_sys(v + 2 * r);
-            b += ld_relaxed_sys(v + 2 * r + 1);
+            a += ld_relaxed_sys(v + PEER_VALS * r);
+            b += ld_relaxed_sys(v + PEER_VALS * r + 1);
+            c += ld_relaxed_sys(v + PEER_VALS * r + 2);
         }
         if (!ok) S->error = 1;
-        sh[0] = a; sh[1] = b;
+        sh[0] = a; sh[1] = b; sh[2] = c;
     }
     __syncthreads();
     s0 = sh[0]; s1 = sh[1];
+    if (s2) *s2 = sh[2];
     __syncthreads();
 }
 
@@ -288,11 +291,11 @@ __device__ __forceinline__ void peer_wait_sums(const PeerComm &pc, unsigned long
 // the flag there.  Ghost rows written earlier by other CTAs of this grid are
 // ordered before the flag by their own system fences (grid_sum2).
 __device__ __forceinline__ void peer_post(const PeerComm &pc, unsigned long long phase, double a,
-                                          double b) {
+                                          double b, double c = 0.0) {
     const int slot = (int)(phase % PEER_SLOTS);
     for (int r = 0; r < pc.nranks; ++r) {
-        double *v = pc.peer_slots[r] + ((size_t)slot * PEER_MAX_RANKS + pc.rank) * 2;
-        v[0] = a; v[1] = b;
+        double *v = pc.peer_slots[r] + ((size_t)slot * PEER_MAX_RANKS + pc.rank) * PEER_VALS;
+        v[0] = a; v[1] = b; v[2] = c;
     }
     __threadfence_system();     // one fence, then plain flag stores: a release per flag would fence each
     for (int r = 0; r < pc.nranks; ++r)
@@ -784,12 +787,18 @@ __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
     const int nb = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
     if (a.defer_x) {
-        // 88-byte iteration (single rank): sum(sol*sol) of the iterate this kernel has just
-        // completed comes out of the same pass as p.q and p.p
-        if (grid_sum3(acc0, acc1, acc2, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm)) {
+        // 88-byte iteration: sum(sol*sol) of the iterate this kernel has just completed
+        // comes out of the same pass as p.q and p.p
+        if (grid_sum3(acc0, acc1, acc2, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm,
+                      a.fuse_scalars == SUMS_PEER)) {
             if (a.fuse_scalars == SUMS_FUSED) {
                 if (!firstit) S->xx = acc2;                          // CG:57
                 scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace, a.hs);
+            } else if (a.fuse_scalars == SUMS_PEER) {
+                // S->xx is set by the update kernel from the all-rank sum posted here
+                S->rho_old = S->rho; S->rho = rr_glob;
+                if (firstit) S->xx = xx_glob;                        // sum(x0*x0), from INIT
+                peer_post(a.pc, a.post_phase, acc0, acc1, acc2);
             } else {
                 S->part[0] = acc0; S->part[1] = acc1; S->part[2] = acc2;
             }
@@ -961,9 +970,10 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     DevScal *S = a.S;
     if (S->finished) return;
     const bool peer = (a.fuse_scalars == SUMS_PEER);
-    double alfa, pq_glob = 0.0, pp_glob = 0.0;
+    const bool r_only = a.r_only != 0;          // 88-byte iteration: x belongs to the SpMV kernel
+    double alfa, pq_glob = 0.0, pp_glob = 0.0, xx_post = 0.0;
     if (peer) {
-        peer_wait_sums(a.pc, a.wait_phase, S, pq_glob, pp_glob);   // dotProd(p,q), sum(p*p)
+        peer_wait_sums(a.pc, a.wait_phase, S, pq_glob, pp_glob, &xx_post);   // dotProd(p,q), sum(p*p)
         alfa = S->rho / pq_glob;                                   // CG:77
     } else {
         alfa = S->alfa;
@@ -986,23 +996,31 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         // just finished, so that the tails of p, q, r it left in L2 are hit
         const long long k0 = 2 * (rev ? a.n2 - 1 - i : i);
         const long long k1 = 2 * (rev ? a.n2 - 1 - (i + stride) : i + stride);
-        double2 x0 = ld2(a.x + k0), p0 = ld2(a.p + k0), r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
-        double2 x1 = ld2(a.x + k1), p1 = ld2(a.p + k1), r1 = ld2(a.r + k1), q1 = ld2(a.q + k1);
-        x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
+        double2 r0 = ld2(a.r + k0), q0 = ld2(a.q + k0), r1 = ld2(a.r + k1), q1 = ld2(a.q + k1);
+        double2 x0 = r0, p0 = r0, x1 = r1, p1 = r1;
+        if (!r_only) { x0 = ld2(a.x + k0); p0 = ld2(a.p + k0); x1 = ld2(a.x + k1); p1 = ld2(a.p + k1); }
         r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
-        x1.x = x1.x + alfa * p1.x; x1.y = x1.y + alfa * p1.y;
         r1.x = r1.x - alfa * q1.x; r1.y = r1.y - alfa * q1.y;
-        st2(a.x + k0, x0); put_r(k0, r0);
-        st2(a.x + k1, x1); put_r(k1, r1);
+        put_r(k0, r0); put_r(k1, r1);
+        if (!r_only) {
+            x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
+            x1.x = x1.x + alfa * p1.x; x1.y = x1.y + alfa * p1.y;
+            st2(a.x + k0, x0); st2(a.x + k1, x1);
+        }
         rr += r0.x * r0.x; rr += r0.y * r0.y; rr += r1.x * r1.x; rr += r1.y * r1.y;
         xx += x0.x * x0.x; xx += x0.y * x0.y; xx += x1.x * x1.x; xx += x1.y * x1.y;
     }
     for (; i < a.n2; i += stride) {
         const long long k0 = 2 * (rev ? a.n2 - 1 - i : i);
-        double2 x0 = ld2(a.x + k0), p0 = ld2(a.p + k0), r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
-        x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
+        double2 r0 = ld2(a.r + k0), q0 = ld2(a.q + k0);
+        double2 x0 = r0, p0 = r0;
+        if (!r_only) { x0 = ld2(a.x + k0); p0 = ld2(a.p + k0); }
         r0.x = r0.x - alfa * q0.x; r0.y = r0.y - alfa * q0.y;
-        st2(a.x + k0, x0); put_r(k0, r0);
+        put_r(k0, r0);
+        if (!r_only) {
+            x0.x = x0.x + alfa * p0.x; x0.y = x0.y + alfa * p0.y;
+            st2(a.x + k0, x0);
+        }
         rr += r0.x * r0.x; rr += r0.y * r0.y;
         xx += x0.x * x0.x; xx += x0.y * x0.y;
     }
@@ -1012,6 +1030,7 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
         } else if (peer) {
             // the stop test of this iteration (CG:55,77,87-90) with the all-rank sums, then
             // this rank's dotProd(r,r) and sum(sol*sol) go to all ranks
+            if (r_only && S->nit > 0) S->xx = xx_post;   // sum(sol*sol) came with p.q and p.p
             scal_after_spmv(S, pq_glob, pp_glob, a.g.n_glob, a.np.tol2, a.trace, nullptr);
             S->finished = S->done;
             peer_post(a.pc, a.post_phase, rr, xx);
