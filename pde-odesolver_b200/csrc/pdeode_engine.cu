@@ -258,6 +258,10 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         PersistArgs pa{};
         pa.st = stencil_args(c);
         pa.st.wait_phase = c->phase;             // posted by the INIT just launched
+        // the 88-byte iteration also exists inside the persistent solve, but measured slower
+        // there (its phase B re-reads p and q it has just written, L2-hot): 9.1e10 against
+        // 1.10e11 on 2 GPUs at 4096^2, 3.9e9 against 4.5e9 at 256^2.  Off unless asked for.
+        pa.st.defer_x = c->cfg.persist_defer ? 1 : 0;
         pa.x = x;
         pa.pbuf[0] = c->pbuf[0]; pa.pbuf[1] = c->pbuf[1]; pa.ip = c->ip;
         pa.red = c->red; pa.bar = c->bar;
@@ -522,7 +526,7 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     CK(cudaMalloc(&c->partials, sizeof(double) * 8 * (size_t)c->max_blocks));
     {
         const size_t G = (size_t)std::max(1, c->cfg.p_nstrips * c->cfg.p_nchunks);
-        CK(cudaMalloc(&c->red, sizeof(double) * 4 * G));
+        CK(cudaMalloc(&c->red, sizeof(double) * 6 * G));
         CK(cudaMalloc(&c->bar, 2 * sizeof(unsigned int)));
         CK(cudaMemset(c->bar, 0, 2 * sizeof(unsigned int)));
     }
@@ -974,7 +978,9 @@ int pdeode_engine_info(const pdeode_ctx *c, char *buf, int len) {
              "defer_x=%d kb_reverse=%d exchange=%s",
              c->cfg.variant == 1 ? "bulk-async" : "register-staged", c->cfg.BS, c->cfg.TR,
              c->cfg.DEPTH, c->cfg.i_BS, c->cfg.i_TR, c->cfg.persist,
-             c->cfg.p_nstrips * c->cfg.p_nchunks, defer_x(c) ? 1 : 0, c->cfg.kb_reverse,
+             c->cfg.p_nstrips * c->cfg.p_nchunks,
+             (c->cfg.persist && sums_mode(c) != SUMS_RAW ? c->cfg.persist_defer != 0 : defer_x(c)) ? 1 : 0,
+             c->cfg.kb_reverse,
              !multi(c) ? "none" : (c->peer ? "peer" : "nccl"));
     return PDEODE_OK;
 }

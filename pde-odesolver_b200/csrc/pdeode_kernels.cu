@@ -1119,20 +1119,25 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int G, 
 // barrier, then every CTA adds all partials in the same fixed order -- every
 // CTA (and, in peer mode, every rank) ends up with the same bits, so each can
 // take the stop decision on its own.  red: [2][G] doubles.
-__device__ __forceinline__ void grid_allsum2(double &a, double &b, double *red, unsigned int *bar,
-                                             int G, double *sm, double *s_tot, bool sys) {
+__device__ __forceinline__ void grid_allsum3(double &a, double &b, double &c, double *red,
+                                             unsigned int *bar, int G, double *sm, double *s_tot,
+                                             bool sys) {
+    double z = 0.0;
     block_sum2(a, b, sm);
-    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; }
+    block_sum2(c, z, sm);
+    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; red[2 * G + blockIdx.x] = c; }
     grid_barrier(bar, (unsigned int)G, sys);
-    double x = 0.0, y = 0.0;
+    double x = 0.0, y = 0.0, w = 0.0, z2 = 0.0;
     for (int i = threadIdx.x; i < G; i += blockDim.x) {
         x += __ldcg(red + i);
         y += __ldcg(red + G + i);
+        w += __ldcg(red + 2 * G + i);
     }
     block_sum2(x, y, sm);
-    if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; }
+    block_sum2(w, z2, sm);
+    if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; s_tot[2] = w; }
     __syncthreads();
-    a = s_tot[0]; b = s_tot[1];
+    a = s_tot[0]; b = s_tot[1]; c = s_tot[2];
     __syncthreads();
 }
 
@@ -1152,11 +1157,12 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
     constexpr int TC = Ring<BS, DEPTH>::TC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double sm[64];
-    __shared__ double s_tot[2];
+    __shared__ double s_tot[3];
     Ring<BS, DEPTH> R;
     R.carve(smem_raw);
 
     const StencilArgs &a = A.st;
+    const bool defer = a.defer_x != 0;     // 88-byte iteration: x += alfa p rides in phase A
     DevScal *S = a.S;
     const GridDesc g = a.g;
     const int G = gridDim.x;
@@ -1195,25 +1201,29 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
         const double *p_in = A.pbuf[ip];
         double *p_out = A.pbuf[ip ^ 1];
         // ---- phase A
-        double acc0 = 0.0, acc1 = 0.0;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0;
         if (tid >= BS) {
             if (tid == BS) {
-                asm volatile("fence.proxy.async;" ::: "memory");     // r, p were written by plain stores
-                bulk_produce<BS, DEPTH>(R, g, a.r, p_in, a.d, a.ac, firstit, jt, i_begin, i_end, K);
+                asm volatile("fence.proxy.async;" ::: "memory");     // r, p, x were written by plain stores
+                bulk_produce<BS, DEPTH>(R, g, a.r, p_in, a.d, a.ac, firstit, jt, i_begin, i_end, K,
+                                        (defer && !firstit) ? A.x : nullptr);
             }
         } else {
+            // alfa still holds the previous iteration's value here
             bulk_consume<BS, DEPTH>(R, g, a.np.h, p_out, a.q, firstit, beta, jt, i_begin, i_end, K,
-                                    a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1);
+                                    a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1,
+                                    defer ? A.x : nullptr, alfa, &acc2);
         }
         K += (i_end - i_begin) + 2;
-        grid_allsum2(acc0, acc1, A.red + (size_t)sel * 2 * G, A.bar, G, sm, s_tot, false);
+        grid_allsum3(acc0, acc1, acc2, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, false);
         sel ^= 1;
         if (peer) {
             ++ph;
-            if (blockIdx.x == 0 && tid == 0) peer_post(a.pc, ph, acc0, acc1);
-            peer_wait_sums(a.pc, ph, S, acc0, acc1);
+            if (blockIdx.x == 0 && tid == 0) peer_post(a.pc, ph, acc0, acc1, acc2);
+            peer_wait_sums(a.pc, ph, S, acc0, acc1, &acc2);
         }
         pq = acc0; pp = acc1;
+        if (defer && !firstit) xx = acc2;                            // CG:57
         alfa = rho / pq;                                             // CG:77
         err2 = fabs(alfa) * sqrt(pp) / n_glob;                       // CG:87
         normx = sqrt(xx) / n_glob;                                   // CG:57
@@ -1225,8 +1235,20 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
             t[0] = rho; t[1] = pq; t[2] = alfa; t[3] = err2; t[4] = normx;
         }
         // ---- phase B: my own cells (the ones whose p and q I just wrote)
-        double rr = 0.0, xn = 0.0;
-        if (worker) {
+        double rr = 0.0, xn = 0.0, zz = 0.0;
+        if (worker && defer) {
+            long long off = (long long)i_begin * g.P + j0;
+            for (int i = i_begin; i < i_end; ++i, off += g.P) {
+                double2 r2 = ld2(a.r + off);
+                const double2 q2 = ld2(a.q + off);
+                r2.x = r2.x - alfa * q2.x; r2.y = r2.y - alfa * q2.y;  // CG:81
+                st2(a.r + off, r2);
+                if (up && i == 0) st2(up + j0, r2);
+                if (dn && i == g.rows - 1) st2(dn + j0, r2);
+                rr += r2.x * r2.x; rr += r2.y * r2.y;
+            }
+            asm volatile("fence.proxy.async;" ::: "memory");
+        } else if (worker) {
             long long off = (long long)i_begin * g.P + j0;
             auto upd = [&](int i, long long o, double2 x2, double2 p2, double2 r2, double2 q2) {
                 x2.x = x2.x + alfa * p2.x; x2.y = x2.y + alfa * p2.y;  // CG:80
@@ -1253,16 +1275,28 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
         }
         // only CTAs that stored into a neighbour GPU need the system-wide fence
         const bool wrote_peer = (up && i_begin == 0) || (dn && i_end == g.rows);
-        grid_allsum2(rr, xn, A.red + (size_t)sel * 2 * G, A.bar, G, sm, s_tot, wrote_peer);
+        grid_allsum3(rr, xn, zz, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, wrote_peer);
         sel ^= 1;
         if (peer) {
             ++ph;
             if (blockIdx.x == 0 && tid == 0) peer_post(a.pc, ph, rr, xn);
             peer_wait_sums(a.pc, ph, S, rr, xn);
         }
-        rho_old = rho; rho = rr; xx = xn;                            // CG:56,59,57
+        rho_old = rho; rho = rr;                                     // CG:56,59
+        if (!defer) xx = xn;                                         // CG:57
         ip ^= 1;
         if (stop != 0) break;
+    }
+    if (defer && worker) {
+        // the last iteration's sol += alfa p (CG:80), on my own cells
+        const double *p_last = A.pbuf[ip];
+        long long off = (long long)i_begin * g.P + j0;
+        for (int i = i_begin; i < i_end; ++i, off += g.P) {
+            double2 x2 = ld2(A.x + off);
+            const double2 p2 = ld2(p_last + off);
+            x2.x = x2.x + alfa * p2.x; x2.y = x2.y + alfa * p2.y;
+            st2(A.x + off, x2);
+        }
     }
     if (blockIdx.x == 0 && tid == 0) {
         S->nit = it; S->stop = stop; S->done = 1; S->finished = 1;
@@ -1657,6 +1691,8 @@ LaunchCfg launch_config(const GridDesc &g) {
     c.kb_reverse = 1;
     // 88-byte iteration (one GPU, kernel-per-phase engine): 6.53e10 against 6.2e10 at 4096^2
     c.defer_x = 1;
+    c.persist_defer = 0;
+    if (const char *e = getenv("PDEODE_PERSIST_DEFER")) c.persist_defer = atoi(e) != 0;
     if (const char *e = getenv("PDEODE_DEFER_X")) c.defer_x = atoi(e) != 0;
     // INIT (sweep at 4096^2): bulk BS 128 x 32 rows 0.200 ms, BS 256 x 64 rows 0.322 ms
     c.i_BS = c.BS > 128 ? 128 : c.BS;
