@@ -619,7 +619,7 @@ __device__ __forceinline__ void bulk_produce(const Ring<BS, DEPTH> &R, const Gri
 
 // Consumers: p = r + beta p ; q = A p on rows [i_begin, i_end) of one strip;
 // adds p.q and p.p of those rows to acc0 / acc1.
-template <int BS, int DEPTH>
+template <int BS, int DEPTH, bool DEFER = false>
 __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const GridDesc &g,
                                              double h, double *p_out, double *q_out,
                                              bool firstit, double beta, int jt, int i_begin,
@@ -645,7 +645,7 @@ __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const Gri
     // fetch one staged row into (v, d, ac, ve, de)
     // deferred update (the 88-byte iteration): x += alfa_prev * p_prev rides along here,
     // on the cells this thread owns, using the p_prev it reads anyway
-    const bool defer = (xdef != nullptr) && !firstit;
+    const bool defer = DEFER && (xdef != nullptr) && !firstit;
     double2 pC = make_double2(0.0, 0.0), pS = pC, pdum = pC;
     double2 xC = make_double2(0.0, 0.0), xS = xC, xdum = xC;
     auto take = [&](long long kk, double2 &v, double2 &d, double2 &ac, double &ve, double &de,
@@ -743,8 +743,11 @@ __device__ __forceinline__ void bulk_consume(const Ring<BS, DEPTH> &R, const Gri
     if (ghost_bot && i_end == g.rows && inrow) st2(p_out + off, vC);
 }
 
-template <int BS, int DEPTH>
-__global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
+// DEFER = the 88-byte iteration (x += alfa p of the previous iteration rides along); kept out
+// of the plain instantiation so that it does not pay the registers.
+template <int BS, int DEPTH, bool DEFER>
+__global__ void __launch_bounds__(BS + 32, (BS == 256 ? 2 : (BS == 128 ? 3 : 6)))
+k_spmv_bulk(const StencilArgs a) {
     constexpr int TC = Ring<BS, DEPTH>::TC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double sm[64];
@@ -777,16 +780,16 @@ __global__ void __launch_bounds__(BS + 32) k_spmv_bulk(const StencilArgs a) {
     if (tid >= BS) {
         if (tid == BS)
             bulk_produce<BS, DEPTH>(R, g, a.r, a.p_in, a.d, a.ac, firstit, jt, i_begin, i_end, 0,
-                                    (a.defer_x && !firstit) ? a.x : nullptr);
+                                    (DEFER && !firstit) ? a.x : nullptr);
     } else {
-        bulk_consume<BS, DEPTH>(R, g, a.np.h, a.p, a.q, firstit, beta, jt, i_begin, i_end, 0,
-                                a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1,
-                                a.defer_x ? a.x : nullptr, alfa_prev, &acc2);
+        bulk_consume<BS, DEPTH, DEFER>(R, g, a.np.h, a.p, a.q, firstit, beta, jt, i_begin, i_end, 0,
+                                       a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1,
+                                       DEFER ? a.x : nullptr, alfa_prev, &acc2);
     }
 
     const int nb = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
-    if (a.defer_x) {
+    if (DEFER) {
         // 88-byte iteration: sum(sol*sol) of the iterate this kernel has just completed
         // comes out of the same pass as p.q and p.p
         if (grid_sum3(acc0, acc1, acc2, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm,
@@ -1119,23 +1122,65 @@ __device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int G, 
 // barrier, then every CTA adds all partials in the same fixed order -- every
 // CTA (and, in peer mode, every rank) ends up with the same bits, so each can
 // take the stop decision on its own.  red: [2][G] doubles.
-__device__ __forceinline__ void grid_allsum3(double &a, double &b, double &c, double *red,
-                                             unsigned int *bar, int G, double *sm, double *s_tot,
-                                             bool sys) {
-    double z = 0.0;
+// Grid-wide sum of a pair: every CTA stores its partial, all meet at the
+// barrier, then every CTA adds all partials in the same fixed order -- every
+// CTA (and, in peer mode, every rank) ends up with the same bits, so each can
+// take the stop decision on its own.  red: [2][G] doubles.  (Measured against a
+// variant where only warp 0 re-adds the partials: this one is faster, 1.93e11
+// against 1.63e11 on 4 GPUs at 4096^2.)
+__device__ __forceinline__ void grid_allsum2(double &a, double &b, double *red, unsigned int *bar,
+                                             int G, double *sm, double *s_tot, bool sys) {
     block_sum2(a, b, sm);
-    block_sum2(c, z, sm);
-    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; red[2 * G + blockIdx.x] = c; }
+    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; }
     grid_barrier(bar, (unsigned int)G, sys);
-    double x = 0.0, y = 0.0, w = 0.0, z2 = 0.0;
+    double x = 0.0, y = 0.0;
     for (int i = threadIdx.x; i < G; i += blockDim.x) {
         x += __ldcg(red + i);
         y += __ldcg(red + G + i);
-        w += __ldcg(red + 2 * G + i);
     }
     block_sum2(x, y, sm);
-    block_sum2(w, z2, sm);
-    if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; s_tot[2] = w; }
+    if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; }
+    __syncthreads();
+    a = s_tot[0]; b = s_tot[1];
+    __syncthreads();
+}
+
+// Sum of a triple over the block with one barrier pair; result in thread 0.  sm: 96 doubles.
+__device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double *sm) {
+    const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    if (lane == 0) { sm[w] = a; sm[32 + w] = b; sm[64 + w] = c; }
+    __syncthreads();
+    if (w == 0) {
+        a = (lane < nw) ? sm[lane] : 0.0;
+        b = (lane < nw) ? sm[32 + lane] : 0.0;
+        c = (lane < nw) ? sm[64 + lane] : 0.0;
+        a = warp_sum(a); b = warp_sum(b); c = warp_sum(c);
+    }
+}
+
+// Grid-wide sum of a triple: every CTA stores its partial, all meet at the
+// barrier, then warp 0 of every CTA adds all partials in the same fixed order
+// (lane l takes partials l, l+32, ...; then a shuffle tree) -- every CTA, and
+// in peer mode every rank, ends up with the same bits, so each can take the
+// stop decision on its own.  red: [3][G] doubles, sm: 96 doubles.
+__device__ __forceinline__ void grid_allsum3(double &a, double &b, double &c, double *red,
+                                             unsigned int *bar, int G, double *sm, double *s_tot,
+                                             bool sys) {
+    block_sum3(a, b, c, sm);
+    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; red[2 * G + blockIdx.x] = c; }
+    grid_barrier(bar, (unsigned int)G, sys);
+    if (threadIdx.x < 32) {
+        double x = 0.0, y = 0.0, w = 0.0;
+        for (int i = threadIdx.x; i < G; i += 32) {
+            x += __ldcg(red + i);
+            y += __ldcg(red + G + i);
+            w += __ldcg(red + 2 * G + i);
+        }
+        x = warp_sum(x); y = warp_sum(y); w = warp_sum(w);
+        if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; s_tot[2] = w; }
+    }
     __syncthreads();
     a = s_tot[0]; b = s_tot[1]; c = s_tot[2];
     __syncthreads();
@@ -1152,17 +1197,18 @@ __device__ __forceinline__ void grid_allsum3(double &a, double &b, double &c, do
 // neighbours' ghost rows.  Used where launch latency would dominate (small
 // grids, thin slabs of a multi-GPU run); results are bit-identical to the
 // kernel-per-phase path only up to the order of the partial sums.
-template <int BS, int DEPTH>
-__global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
+template <int BS, int DEPTH, bool DEFER>
+__global__ void __launch_bounds__(BS + 32, (BS == 256 ? 2 : (BS == 128 ? 3 : 5)))
+k_cg_persist(const PersistArgs A) {
     constexpr int TC = Ring<BS, DEPTH>::TC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ double sm[64];
+    __shared__ double sm[96];
     __shared__ double s_tot[3];
     Ring<BS, DEPTH> R;
     R.carve(smem_raw);
 
     const StencilArgs &a = A.st;
-    const bool defer = a.defer_x != 0;     // 88-byte iteration: x += alfa p rides in phase A
+    constexpr bool defer = DEFER;          // 88-byte iteration: x += alfa p rides in phase A
     DevScal *S = a.S;
     const GridDesc g = a.g;
     const int G = gridDim.x;
@@ -1210,12 +1256,13 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
             }
         } else {
             // alfa still holds the previous iteration's value here
-            bulk_consume<BS, DEPTH>(R, g, a.np.h, p_out, a.q, firstit, beta, jt, i_begin, i_end, K,
+            bulk_consume<BS, DEPTH, DEFER>(R, g, a.np.h, p_out, a.q, firstit, beta, jt, i_begin, i_end, K,
                                     a.write_ghost_top != 0, a.write_ghost_bot != 0, acc0, acc1,
                                     defer ? A.x : nullptr, alfa, &acc2);
         }
         K += (i_end - i_begin) + 2;
-        grid_allsum3(acc0, acc1, acc2, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, false);
+        if (defer) grid_allsum3(acc0, acc1, acc2, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, false);
+        else grid_allsum2(acc0, acc1, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, false);
         sel ^= 1;
         if (peer) {
             ++ph;
@@ -1235,7 +1282,7 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
             t[0] = rho; t[1] = pq; t[2] = alfa; t[3] = err2; t[4] = normx;
         }
         // ---- phase B: my own cells (the ones whose p and q I just wrote)
-        double rr = 0.0, xn = 0.0, zz = 0.0;
+        double rr = 0.0, xn = 0.0;
         if (worker && defer) {
             long long off = (long long)i_begin * g.P + j0;
             for (int i = i_begin; i < i_end; ++i, off += g.P) {
@@ -1275,7 +1322,7 @@ __global__ void __launch_bounds__(BS + 32) k_cg_persist(const PersistArgs A) {
         }
         // only CTAs that stored into a neighbour GPU need the system-wide fence
         const bool wrote_peer = (up && i_begin == 0) || (dn && i_end == g.rows);
-        grid_allsum3(rr, xn, zz, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, wrote_peer);
+        grid_allsum2(rr, xn, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, wrote_peer);
         sel ^= 1;
         if (peer) {
             ++ph;
@@ -1594,14 +1641,23 @@ constexpr int PERSIST_DEPTH = 4;
 template <int BS>
 static int persist_occupancy() {
     constexpr size_t smem = Ring<BS, PERSIST_DEPTH>::BYTES;
-    if (cudaFuncSetAttribute(k_cg_persist<BS, PERSIST_DEPTH>,
+    // the 88-byte instantiation needs more registers; size the grid for whichever fits fewer
+    if (cudaFuncSetAttribute(k_cg_persist<BS, PERSIST_DEPTH, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
+    if (cudaFuncSetAttribute(k_cg_persist<BS, PERSIST_DEPTH, false>,
                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
     int n = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cg_persist<BS, PERSIST_DEPTH>, BS + 32,
-                                                      smem) != cudaSuccess) {
+    const bool want_defer = getenv("PDEODE_PERSIST_DEFER") && atoi(getenv("PDEODE_PERSIST_DEFER")) != 0;
+    cudaError_t e = want_defer
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cg_persist<BS, PERSIST_DEPTH, true>, BS + 32, smem)
+        : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cg_persist<BS, PERSIST_DEPTH, false>, BS + 32, smem);
+    if (e != cudaSuccess) {
         cudaGetLastError();
         return 0;
     }
@@ -1617,7 +1673,9 @@ static int persist_ctas_per_sm(int bs) {
 template <int BS>
 static cudaError_t launch_cg_persist_t(const PersistArgs &a, cudaStream_t st) {
     void *args[] = {const_cast<PersistArgs *>(&a)};
-    return cudaLaunchCooperativeKernel((const void *)k_cg_persist<BS, PERSIST_DEPTH>,
+    const void *fn = a.st.defer_x ? (const void *)k_cg_persist<BS, PERSIST_DEPTH, true>
+                                  : (const void *)k_cg_persist<BS, PERSIST_DEPTH, false>;
+    return cudaLaunchCooperativeKernel(fn,
                                        dim3(a.nstrips * a.nchunks), dim3(BS + 32), args,
                                        Ring<BS, PERSIST_DEPTH>::BYTES, st);
 }
@@ -1760,13 +1818,17 @@ static cudaError_t launch_spmv_bulk(const StencilArgs &a, cudaStream_t st) {
     constexpr size_t smem = Ring<BS, DEPTH>::BYTES;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaError_t e = cudaFuncSetAttribute(k_spmv_bulk<BS, DEPTH>,
+        cudaError_t e = cudaFuncSetAttribute(k_spmv_bulk<BS, DEPTH, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(k_spmv_bulk<BS, DEPTH, true>,
+                                 cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr_set = true;
     }
     dim3 grid(cdiv(a.g.P, TC), cdiv(a.g.rows, a.TR));
-    k_spmv_bulk<BS, DEPTH><<<grid, BS + 32, smem, st>>>(a);
+    if (a.defer_x) k_spmv_bulk<BS, DEPTH, true><<<grid, BS + 32, smem, st>>>(a);
+    else k_spmv_bulk<BS, DEPTH, false><<<grid, BS + 32, smem, st>>>(a);
     return cudaGetLastError();
 }
 
