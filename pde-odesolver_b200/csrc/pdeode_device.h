@@ -88,13 +88,6 @@ struct PeerComm {
     int rows_up;                               // local rows of rank-1 (its bottom ghost row index)
 };
 
-struct HostStatus {           // written by the device into mapped host memory
-    volatile long long seq_done;   // (seq << 1) | finished
-    volatile long long nit;
-    volatile long long seq_picard; // seq of the last completed solveC_diff
-    volatile double diffC, diffM;
-};
-
 enum { TICKET_STENCIL = 0, TICKET_UPDATE = 1, TICKET_SOLVEC = 2, TICKET_MASS = 3 };
 
 // Arguments of the 5-point marching kernel.
@@ -103,7 +96,6 @@ struct StencilArgs {
     NumParams np;
     DevScal *S;
     double *partials;      // [2][maxblocks]
-    HostStatus *hs;        // may be null
     double *trace;         // may be null; 5 doubles per CG iteration
     // INIT: x0 -> (ac, r, x);   CG: (r, p) -> (p, q)
     const double *x0, *d, *Cc, *Mprev;
@@ -138,7 +130,6 @@ struct UpdateArgs {
     GridDesc g;
     DevScal *S;
     double *partials;
-    HostStatus *hs;
     double *x, *r;
     const double *p, *q;
     long long n2;          // number of double2 elements to stream (rows*P/2)
@@ -157,7 +148,6 @@ struct SolveCArgs {
     NumParams np;
     DevScal *S;
     double *partials;
-    HostStatus *hs;
     const double *Mprev, *Mnew, *Cprev, *Ccur, *Mcur;
     double *Cnew;
     long long n2;
@@ -198,11 +188,9 @@ cudaError_t launch_rowmeans(const GridDesc &g, const double *M, const double *C,
 // scalar steps for the multi-rank path (sums already all-reduced into S->part)
 cudaError_t launch_scal_after_init(DevScal *S, cudaStream_t st);
 cudaError_t launch_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace,
-                                   HostStatus *hs, long long seq, cudaStream_t st);
-cudaError_t launch_scal_after_update(DevScal *S, HostStatus *hs, long long seq,
-                                     cudaStream_t st);
-cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq,
-                                     cudaStream_t st);
+                                   cudaStream_t st);
+cudaError_t launch_scal_after_update(DevScal *S, cudaStream_t st);
+cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, cudaStream_t st);
 // Launch shape of the 5-point kernels for one context.
 struct LaunchCfg {
     int BS, TR, DEPTH, variant;

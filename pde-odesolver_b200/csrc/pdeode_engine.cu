@@ -173,7 +173,7 @@ int wait_snapshot(pdeode_ctx *c, int slot) {
 StencilArgs stencil_args(pdeode_ctx *c) {
     StencilArgs a{};
     a.g = c->g; a.np = c->np; a.S = c->S; a.partials = c->partials;
-    a.hs = nullptr; a.trace = c->trace_cap > 0 ? c->trace : nullptr;
+    a.trace = c->trace_cap > 0 ? c->trace : nullptr;
     a.d = c->d; a.ac = c->ac; a.r = c->r; a.q = c->q;
     a.p_in = c->pbuf[c->ip]; a.p = c->pbuf[c->ip ^ 1];
     a.TR = c->cfg.TR; a.BS = c->cfg.BS; a.DEPTH = c->cfg.DEPTH; a.variant = c->cfg.variant;
@@ -201,11 +201,11 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     if (mode == SUMS_RAW) {
         int rc = allreduce_part(c, 2);
         if (rc) return rc;
-        CK(launch_scal_after_spmv(c->S, c->g, c->np.tol2, a.trace, nullptr, c->seq, c->stream));
+        CK(launch_scal_after_spmv(c->S, c->g, c->np.tol2, a.trace, c->stream));
         c->launches++;
     }
     UpdateArgs u{};
-    u.g = c->g; u.S = c->S; u.partials = c->partials; u.hs = nullptr;
+    u.g = c->g; u.S = c->S; u.partials = c->partials;
     u.x = x; u.r = c->r; u.p = c->p; u.q = c->q;
     u.n2 = (long long)c->g.rows * c->g.P / 2;
     u.fuse_scalars = mode;
@@ -221,7 +221,7 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     if (mode == SUMS_RAW) {
         int rc = allreduce_part(c, 2);
         if (rc) return rc;
-        CK(launch_scal_after_update(c->S, nullptr, c->seq, c->stream));
+        CK(launch_scal_after_update(c->S, c->stream));
         c->launches++;
         rc = halo_exchange(c, c->r);
         if (rc) return rc;
@@ -814,7 +814,7 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         int icnew = 0;
         while (icnew == c->iCprev || icnew == c->iC) icnew++;
         SolveCArgs s{};
-        s.g = c->g; s.np = c->np; s.S = c->S; s.partials = c->partials; s.hs = nullptr;
+        s.g = c->g; s.np = c->np; s.S = c->S; s.partials = c->partials;
         s.Mprev = c->Mb[c->iMprev]; s.Mnew = c->Mb[inew]; s.Cprev = c->Cb[c->iCprev];
         s.Ccur = c->Cb[c->iC]; s.Mcur = c->Mb[c->iM]; s.Cnew = c->Cb[icnew];
         s.n2 = (long long)c->g.rows * c->g.P / 2;
@@ -824,7 +824,7 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         c->launches++;
         if (multi(c)) {
             if ((rc = allreduce_part(c, 2))) return rc;
-            CK(launch_scal_after_solvec(c->S, c->g, nullptr, c->seq, c->stream));
+            CK(launch_scal_after_solvec(c->S, c->g, c->stream));
             c->launches++;
         }
         if ((rc = snapshot(c, 0))) return rc;

@@ -174,8 +174,7 @@ __device__ __forceinline__ void scal_after_init(DevScal *S, double rr, double xx
 
 // CG:55,77,87-90
 __device__ __forceinline__ void scal_after_spmv(DevScal *S, double pq, double pp,
-                                                double n_glob, double tol2, double *trace,
-                                                HostStatus *hs) {
+                                                double n_glob, double tol2, double *trace) {
     const long long nit = S->nit + 1;                      // CG:55
     const double alfa = S->rho / pq;                       // CG:77
     const double err2 = fabs(alfa) * sqrt(pp) / n_glob;    // CG:87
@@ -190,47 +189,33 @@ __device__ __forceinline__ void scal_after_spmv(DevScal *S, double pq, double pp
     }
     S->pq = pq; S->pp = pp; S->alfa = alfa; S->err2 = err2; S->normx = normx;
     S->nit = nit; S->stop = stop; S->done = (stop != 0);
-    if (hs) hs->nit = nit;
 }
 
-__device__ __forceinline__ void scal_after_update(DevScal *S, double rr, double xx,
-                                                  HostStatus *hs, long long seq) {
+__device__ __forceinline__ void scal_after_update(DevScal *S, double rr, double xx) {
     S->rho_old = S->rho;  // CG:56
     S->rho = rr;          // CG:59 of the next iteration
     S->xx = xx;           // CG:57 of the next iteration
     S->finished = S->done;
-    if (hs) {
-        __threadfence_system();
-        hs->seq_done = (seq << 1) | (long long)S->finished;
-    }
 }
 
 // P:961
 __device__ __forceinline__ void scal_after_solvec(DevScal *S, double dC, double dM,
-                                                  double n_glob, HostStatus *hs,
-                                                  long long seq) {
+                                                  double n_glob) {
     S->diffC = dC / n_glob;
     S->diffM = dM / n_glob;
-    if (hs) {
-        hs->diffC = S->diffC;
-        hs->diffM = S->diffM;
-        __threadfence_system();
-        hs->seq_picard = seq;
-    }
 }
 
 __global__ void k_scal_after_init(DevScal *S) { scal_after_init(S, S->part[0], S->part[1]); }
-__global__ void k_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace,
-                                  HostStatus *hs) {
+__global__ void k_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace) {
     if (S->done) return;
-    scal_after_spmv(S, S->part[0], S->part[1], g.n_glob, tol2, trace, hs);
+    scal_after_spmv(S, S->part[0], S->part[1], g.n_glob, tol2, trace);
 }
-__global__ void k_scal_after_update(DevScal *S, HostStatus *hs, long long seq) {
+__global__ void k_scal_after_update(DevScal *S) {
     if (S->finished) return;
-    scal_after_update(S, S->part[0], S->part[1], hs, seq);
+    scal_after_update(S, S->part[0], S->part[1]);
 }
-__global__ void k_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq) {
-    scal_after_solvec(S, S->part[0], S->part[1], g.n_glob, hs, seq);
+__global__ void k_scal_after_solvec(DevScal *S, GridDesc g) {
+    scal_after_solvec(S, S->part[0], S->part[1], g.n_glob);
 }
 
 // ---------------------------------------------------------------- peer-memory exchange
@@ -239,9 +224,6 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     unsigned long long v;
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v) {
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
@@ -501,7 +483,7 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
                   a.fuse_scalars == SUMS_PEER)) {
         if (a.fuse_scalars == SUMS_FUSED) {
             if (MODE == MODE_INIT) scal_after_init(S, acc0, acc1);
-            else scal_after_spmv(S, acc0, acc1, g.n_glob, np.tol2, a.trace, a.hs);
+            else scal_after_spmv(S, acc0, acc1, g.n_glob, np.tol2, a.trace);
         } else if (a.fuse_scalars == SUMS_PEER && MODE == MODE_INIT) {
             // rho and sum(sol*sol) become known to every rank once all have posted; the
             // first K_A adds the slots.  Local part of CG:53 happens here.
@@ -796,7 +778,7 @@ k_spmv_bulk(const StencilArgs a) {
                       a.fuse_scalars == SUMS_PEER)) {
             if (a.fuse_scalars == SUMS_FUSED) {
                 if (!firstit) S->xx = acc2;                          // CG:57
-                scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace, a.hs);
+                scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace);
             } else if (a.fuse_scalars == SUMS_PEER) {
                 // S->xx is set by the update kernel from the all-rank sum posted here
                 S->rho_old = S->rho; S->rho = rr_glob;
@@ -811,7 +793,7 @@ k_spmv_bulk(const StencilArgs a) {
     if (grid_sum2(acc0, acc1, a.partials, nb, bid, &S->ticket[TICKET_STENCIL], sm,
                   a.fuse_scalars == SUMS_PEER)) {
         if (a.fuse_scalars == SUMS_FUSED) {
-            scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace, a.hs);
+            scal_after_spmv(S, acc0, acc1, g.n_glob, a.np.tol2, a.trace);
         } else if (a.fuse_scalars == SUMS_PEER) {
             // close the previous phase (CG:56,57,59) now that every CTA has used rho_old,
             // then hand this rank's p.q and p.p to all ranks
@@ -1029,12 +1011,12 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     }
     if (grid_sum2(rr, xx, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_UPDATE], sm, peer)) {
         if (a.fuse_scalars == SUMS_FUSED) {
-            scal_after_update(S, rr, xx, a.hs, a.seq);
+            scal_after_update(S, rr, xx);
         } else if (peer) {
             // the stop test of this iteration (CG:55,77,87-90) with the all-rank sums, then
             // this rank's dotProd(r,r) and sum(sol*sol) go to all ranks
             if (r_only && S->nit > 0) S->xx = xx_post;   // sum(sol*sol) came with p.q and p.p
-            scal_after_spmv(S, pq_glob, pp_glob, a.g.n_glob, a.np.tol2, a.trace, nullptr);
+            scal_after_spmv(S, pq_glob, pp_glob, a.g.n_glob, a.np.tol2, a.trace);
             S->finished = S->done;
             peer_post(a.pc, a.post_phase, rr, xx);
         } else {
@@ -1074,7 +1056,7 @@ __global__ void __launch_bounds__(256) k_update_r(const UpdateArgs a) {
     }
     if (grid_sum2(rr, zz, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_UPDATE], sm)) {
         if (a.fuse_scalars == SUMS_FUSED)
-            scal_after_update(S, rr, S->xx, a.hs, a.seq);  // sum(sol*sol) is the SpMV kernel's now
+            scal_after_update(S, rr, S->xx);  // sum(sol*sol) is the SpMV kernel's now
         else
             S->part[0] = rr;
     }
@@ -1387,7 +1369,7 @@ __global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
         dM += v1 ? fabs(mc.y - mn.y) : 0.0;
     }
     if (grid_sum2(dC, dM, a.partials, gridDim.x, blockIdx.x, &a.S->ticket[TICKET_SOLVEC], sm)) {
-        if (a.fuse_scalars) scal_after_solvec(a.S, dC, dM, g.n_glob, a.hs, a.seq);
+        if (a.fuse_scalars) scal_after_solvec(a.S, dC, dM, g.n_glob);
         else { a.S->part[0] = dC; a.S->part[1] = dM; }
     }
 }
@@ -1885,17 +1867,16 @@ cudaError_t launch_scal_after_init(DevScal *S, cudaStream_t st) {
     return cudaGetLastError();
 }
 cudaError_t launch_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace,
-                                   HostStatus *hs, long long, cudaStream_t st) {
-    k_scal_after_spmv<<<1, 1, 0, st>>>(S, g, tol2, trace, hs);
+                                   cudaStream_t st) {
+    k_scal_after_spmv<<<1, 1, 0, st>>>(S, g, tol2, trace);
     return cudaGetLastError();
 }
-cudaError_t launch_scal_after_update(DevScal *S, HostStatus *hs, long long seq, cudaStream_t st) {
-    k_scal_after_update<<<1, 1, 0, st>>>(S, hs, seq);
+cudaError_t launch_scal_after_update(DevScal *S, cudaStream_t st) {
+    k_scal_after_update<<<1, 1, 0, st>>>(S);
     return cudaGetLastError();
 }
-cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, HostStatus *hs, long long seq,
-                                     cudaStream_t st) {
-    k_scal_after_solvec<<<1, 1, 0, st>>>(S, g, hs, seq);
+cudaError_t launch_scal_after_solvec(DevScal *S, GridDesc g, cudaStream_t st) {
+    k_scal_after_solvec<<<1, 1, 0, st>>>(S, g);
     return cudaGetLastError();
 }
 
