@@ -73,6 +73,7 @@ struct pdeode_ctx {
     void *ipc_open[2 * PEER_MAX_RANKS + 2] = {nullptr};
     int n_ipc_open = 0;
     unsigned long long phase = 0;               // id of the last posting kernel launched
+    bool solve_defer = false;                   // the solve in flight uses the 88-byte iteration
     bool pending_persist = false;               // a persistent solve is queued, not yet read back
     int pending_ip0 = 0;
 
@@ -188,7 +189,7 @@ StencilArgs stencil_args(pdeode_ctx *c) {
 // one CG iteration: CG:55-90
 int cg_iteration(pdeode_ctx *c, double *x) {
     const int mode = sums_mode(c);
-    const bool defer = defer_x(c);
+    const bool defer = c->solve_defer;
     StencilArgs a = stencil_args(c);
     a.wait_phase = c->phase;                 // posted by INIT or the previous K_B
     a.post_phase = ++c->phase;
@@ -277,6 +278,11 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         return PDEODE_OK;
     }
 
+    // The 88-byte iteration saves 8 B per cell and iteration and costs one 24 B
+    // pass at the end: worth it from about four iterations on (the previous
+    // step's count for this Picard iterate decides; the same on every rank).
+    c->solve_defer = defer_x(c) && c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)] >= 4;
+
     // CG iterations in chunks; the device flags convergence, later launches
     // of a finished solve return at once.
     const int pred = std::max(1, c->pred[std::min(solve_idx, MAX_PICARD_TRACE - 1)]);
@@ -326,7 +332,7 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     // iteration sits in the buffer given by the parity of nit
     c->ip = ip0 ^ (int)(fin.nit & 1);
     c->p = c->pbuf[c->ip];
-    if (defer_x(c)) {
+    if (c->solve_defer) {
         // the x update of the last iteration was deferred to a kernel that never ran
         CK(launch_xtail(x, c->p, c->S, (long long)c->g.rows * c->g.P / 2, c->stream));
         c->launches++;

@@ -83,6 +83,28 @@ def main():
             print(f"step {k}: N={world} nits {g['nits']} vs 1-GPU {r1['nits']}  relL2 M {eM:.2e} C {eC:.2e} "
                   f"mass {mass} vs {m1} peak {peak} vs {p1} -> {'ok' if good else 'FAIL'}", flush=True)
             ok = ok and good
+    # initial conditions built on the device, slab by slab, and decimated frames
+    rs = np.random.RandomState(1)
+    px, py = rs.rand(9), rs.rand(9) * 0.1
+    for ic in (5, 9, 1):
+        s.set_initial_condition(ic, 0.2, 0.3, px, py)
+        Ml, Cl = s.get_state()
+        fM, fC = s.frame(4)
+        sizes = [((r + 1) * row // world - r * row // world) * col for r in range(world)]
+        Mg = [torch.empty(sz, dtype=torch.float64, device="cuda") for sz in sizes]
+        dist.all_gather(Mg, torch.from_numpy(Ml).cuda())
+        fr = [None] * world
+        dist.all_gather_object(fr, fM)
+        if rank == 0:
+            ref.set_initial_condition(ic, 0.2, 0.3, px, py)
+            M1, _ = ref.get_state()
+            Mall = torch.cat(Mg).cpu().numpy()
+            same = np.array_equal(Mall, M1) if ic != 5 else np.allclose(Mall, M1, rtol=1e-14, atol=0)
+            f1, _ = ref.frame(4)
+            fall = np.concatenate(fr, axis=0)
+            fsame = fall.shape == f1.shape and (np.array_equal(fall, f1) if ic != 5 else np.allclose(fall, f1, rtol=1e-14))
+            print(f"device IC {ic}: fields {'ok' if same else 'FAIL'}, frames {'ok' if fsame else 'FAIL'}", flush=True)
+            ok = ok and same and fsame
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, 0)
     s.close()
