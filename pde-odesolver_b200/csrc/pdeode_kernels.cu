@@ -1717,6 +1717,11 @@ LaunchCfg launch_config(const GridDesc &g) {
     int nch = per_sm * g_num_sms / c.p_nstrips;
     const int by_rows = g.rows / 4 > 0 ? g.rows / 4 : 1;
     if (nch > by_rows) nch = by_rows;
+    // several contexts sharing one GPU (ensembles): leave room for the others' grids
+    if (const char *e = getenv("PDEODE_PERSIST_MAX_CTAS")) {
+        const int cap = atoi(e) / c.p_nstrips;
+        if (cap >= 1 && nch > cap) nch = cap;
+    }
     c.p_nchunks = nch;
     // default: where a CG iteration is short enough for launch latency to matter
     // (measured: one GPU, faster up to 2048^2 and 4 % slower at 4096^2; as a slab of a

@@ -12,8 +12,9 @@
 // DIRNAME (runAll.sh:3-4); the console goes to <name>Output/console.txt.
 // Members are replicas: no communication between them.  They are dealt
 // round-robin over the visible GPUs (PDEODE_DEVICES = "0,1,..." to restrict)
-// and PDEODE_MEMBERS_PER_GPU (default 4) of them run concurrently per GPU,
+// and PDEODE_MEMBERS_PER_GPU (default 8) of them run concurrently per GPU,
 // each on its own context and stream, so that small grids fill the device.
+#include <algorithm>
 #include <atomic>
 #include <cstdio>
 #include <cstdlib>
@@ -56,8 +57,16 @@ int main(int argc, char **argv) {
         }
         for (int i = 0; i < n; ++i) devices.push_back(i);
     }
-    int per_gpu = 4;
+    int per_gpu = 8;     // measured best for 512^2 members on a B200 (profiles/README.md)
     if (const char *m = getenv("PDEODE_MEMBERS_PER_GPU")) per_gpu = atoi(m) > 0 ? atoi(m) : 1;
+
+    // members share a GPU: each persistent solve takes its share of the resident CTAs
+    // (about 5 per SM) instead of all of them, so that their grids run side by side
+    if (!getenv("PDEODE_PERSIST_MAX_CTAS")) {
+        char cap[32];
+        snprintf(cap, sizeof cap, "%d", std::max(64, 148 * 5 / per_gpu));
+        setenv("PDEODE_PERSIST_MAX_CTAS", cap, 1);
+    }
 
     const int nmember = argc - 1;
     std::vector<int> rc((size_t)nmember, -1);
