@@ -200,6 +200,7 @@ struct LaunchCfg {
     int kb_reverse;        // K_B sweeps against K_A's direction
     int defer_x;           // 88-byte iteration: x += alfa p deferred into the next SpMV kernel
     int persist_defer;     // the same inside the persistent solve (measured slower: default 0)
+    int TR_x;              // rows per CTA of the 88-byte SpMV kernel (its optimum is lower)
     int i_BS, i_TR;        // launch shape of the INIT kernel (two IEEE divides per cell: it
                            // wants more warps per SM than the SpMV does)
 };

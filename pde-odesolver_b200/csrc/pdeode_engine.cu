@@ -194,6 +194,7 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     a.wait_phase = c->phase;                 // posted by INIT or the previous K_B
     a.post_phase = ++c->phase;
     a.defer_x = defer ? 1 : 0;
+    if (defer) a.TR = c->cfg.TR_x;
     a.x = x;
     CK(launch_stencil_cg(a, c->stream));
     c->launches++;
@@ -527,7 +528,7 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
 
     c->cfg = launch_config(c->g);
     // the marching kernels never launch more CTAs than stencil_max_blocks(g, TR)
-    c->max_blocks = std::max(stencil_max_blocks(c->g, std::min(c->cfg.TR, c->cfg.i_TR)),
+    c->max_blocks = std::max(stencil_max_blocks(c->g, std::min(std::min(c->cfg.TR, c->cfg.TR_x), c->cfg.i_TR)),
                              std::max(stream_blocks(), 512));
     CK(cudaMalloc(&c->partials, sizeof(double) * 8 * (size_t)c->max_blocks));
     {
@@ -1044,7 +1045,7 @@ int pdeode_time_kernel(pdeode_ctx *c, int kernel, int reps, float *ms_per_launch
         case PDEODE_KERNEL_CG_UPDATE: CK(launch_update(u, c->stream)); break;
         case PDEODE_KERNEL_CG_SPMV_X: {
             StencilArgs ax = a;
-            ax.defer_x = 1; ax.x = u.x; ax.variant = 1;
+            ax.defer_x = 1; ax.x = u.x; ax.variant = 1; ax.TR = c->cfg.TR_x;
             CK(launch_stencil_cg(ax, c->stream));
             break;
         }

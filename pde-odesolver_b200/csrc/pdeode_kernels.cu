@@ -1737,6 +1737,8 @@ LaunchCfg launch_config(const GridDesc &g) {
     // 88-byte iteration (one GPU, kernel-per-phase engine): 6.53e10 against 6.2e10 at 4096^2
     c.defer_x = 1;
     c.persist_defer = 0;
+    // sweep at 4096^2: the 88-byte kernel runs 0.183 ms at 32 rows per CTA, 0.194 ms at 64
+    c.TR_x = c.TR > 32 ? 32 : c.TR;
     if (const char *e = getenv("PDEODE_PERSIST_DEFER")) c.persist_defer = atoi(e) != 0;
     if (const char *e = getenv("PDEODE_DEFER_X")) c.defer_x = atoi(e) != 0;
     // INIT (sweep at 4096^2): bulk BS 128 x 32 rows 0.200 ms, BS 256 x 64 rows 0.322 ms
