@@ -126,6 +126,48 @@ struct PersistArgs {
     int nstrips, nchunks;  // G = nstrips * nchunks CTAs, one tile each
 };
 
+// What one whole-step launch (k_step_persist) reports back: the quantities
+// solveOrder2 keeps per time step (P:702,722-723,730) plus the buffer roles.
+constexpr int STEP_TRACE = 64;
+struct StepOut {
+    long long nit_sum, nit_max;          // P:723, P:722
+    long long nit[STEP_TRACE];           // CG iterations of each solve of the step
+    double diffs[2 * STEP_TRACE];        // (diffC, diffM) after each Picard iterate (P:725-726)
+    int count;                           // countIters (P:730)
+    int cg_cap;                          // some solve ran into nit > maxit (CG:88)
+    int picard_cap;                      // count > cap (P:732)
+    int error;                           // a grid barrier timed out
+    int iM, iC, iMnew, ip;               // buffer roles after the step
+    unsigned long long gen;              // generation of the last grid-wide sum (see step_allsum)
+    unsigned long long seq;              // StepArgs::seq, stored last: the report is complete
+    int nstamps, pad;                    // PDEODE_STEP_STAMPS=1: phase time stamps of CTA 0
+    unsigned long long stamp_ns[48], stamp_clk[48];
+};
+
+// Arguments of the whole time step in one cooperative launch (k_step_persist):
+// D(Mprev), then per Picard iterate the centre diagonal, the CG solve, the C
+// update and the residuals (P:700-742).  One rank only.
+struct StepArgs {
+    StencilArgs st;        // grid, numbers, scalars, d, ac, r, q
+    double *Mb[3], *Cb[3]; // the rotating field buffers
+    int iM, iC;            // current iterate at entry; becomes Mprev / Cprev (P:703-704)
+    int warm;              // 0: first solve ever, x0 = the zeroed buffer iMnew0 (D8)
+    int iMnew0;
+    double *pbuf[2];
+    int ip;
+    double *slots;         // [2][G][4] partial sums (step_allsum)
+    unsigned long long *counter; // arrivals at grid-wide sums since the context was created
+    unsigned long long gen0;     // number of grid-wide sums of earlier launches
+    unsigned int *bar;     // bar[2]: error word
+    int nstrips, nchunks;  // G = nstrips * nchunks CTAs of blockDim.x threads, one tile each
+    int cw;                // threads per row group (strip width / 2); blockDim.x / cw row groups
+    double eSoln;          // P:706
+    int picard_cap;        // P:732
+    StepOut *out;          // mapped host memory
+    int stamps;            // 1: CTA 0 records a time stamp after every phase
+    unsigned long long seq;
+};
+
 struct UpdateArgs {
     GridDesc g;
     DevScal *S;
@@ -203,8 +245,12 @@ struct LaunchCfg {
     int TR_x;              // rows per CTA of the 88-byte SpMV kernel (its optimum is lower)
     int i_BS, i_TR;        // launch shape of the INIT kernel (two IEEE divides per cell: it
                            // wants more warps per SM than the SpMV does)
+    // whole time step in one cooperative launch (small grids, one rank): 0 = off, else
+    // s_nstrips * s_nchunks CTAs of s_BS threads
+    int whole_step, s_BS, s_cw, s_nstrips, s_nchunks;
 };
 cudaError_t launch_cg_persist(const PersistArgs &a, int BS, cudaStream_t st);
+cudaError_t launch_step_persist(const StepArgs &a, int BS, cudaStream_t st);
 // Heuristic defaults for a grid, then PDEODE_BS / PDEODE_TR / PDEODE_DEPTH /
 // PDEODE_VARIANT (reg|bulk) overrides from the environment.
 LaunchCfg launch_config(const GridDesc &g);

@@ -11,6 +11,7 @@
 #include "pdeode_device.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -54,6 +55,14 @@ struct pdeode_ctx {
     DevScal *S = nullptr;
     double *red = nullptr;            // persistent solve: grid-wide reduction buffers
     unsigned int *bar = nullptr;      // persistent solve: grid barrier
+    StepOut *step_out_h = nullptr;    // whole-step launch: its report, mapped host memory
+    StepOut *step_out = nullptr;      // the same, device-side address
+    bool step_poll = true;            // wait for the report by watching its sequence word
+    bool step_stamps = false;         // PDEODE_STEP_STAMPS=1: print CTA 0's phase times of every step to stderr
+    unsigned long long step_seq = 0;
+    double *step_slots = nullptr;     // whole-step launch: partial sums and arrival counter of its grid-wide sums
+    unsigned long long *step_counter = nullptr;
+    unsigned long long step_gen = 0;
     double *partials = nullptr;
     int max_blocks = 0;
     double *trace = nullptr;
@@ -532,10 +541,27 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
                              std::max(stream_blocks(), 512));
     CK(cudaMalloc(&c->partials, sizeof(double) * 8 * (size_t)c->max_blocks));
     {
-        const size_t G = (size_t)std::max(1, c->cfg.p_nstrips * c->cfg.p_nchunks);
+        const size_t G = (size_t)std::max(1, std::max(c->cfg.p_nstrips * c->cfg.p_nchunks,
+                                                      c->cfg.s_nstrips * c->cfg.s_nchunks));
         CK(cudaMalloc(&c->red, sizeof(double) * 6 * G));
-        CK(cudaMalloc(&c->bar, 2 * sizeof(unsigned int)));
-        CK(cudaMemset(c->bar, 0, 2 * sizeof(unsigned int)));
+        CK(cudaMalloc(&c->bar, 4 * sizeof(unsigned int)));
+        CK(cudaMemset(c->bar, 0, 4 * sizeof(unsigned int)));
+    }
+    if (nranks > 1) c->cfg.whole_step = 0;              // one rank only
+    if (c->cfg.whole_step) {
+        // the launch reports straight into mapped host memory: no copy behind the kernel
+        CK(cudaHostAlloc(&c->step_out_h, sizeof(StepOut), cudaHostAllocMapped));
+        memset(c->step_out_h, 0, sizeof(StepOut));
+        CK(cudaHostGetDevicePointer(&c->step_out, c->step_out_h, 0));
+        const char *pe = getenv("PDEODE_STEP_POLL");
+        c->step_poll = !(pe && pe[0] == '0');
+        const char *se = getenv("PDEODE_STEP_STAMPS");
+        c->step_stamps = se && se[0] == '1';
+        const size_t G = (size_t)c->cfg.s_nstrips * c->cfg.s_nchunks;
+        CK(cudaMalloc(&c->step_slots, sizeof(double) * 8 * G));
+        CK(cudaMemset(c->step_slots, 0, sizeof(double) * 8 * G));
+        CK(cudaMalloc(&c->step_counter, sizeof(unsigned long long)));
+        CK(cudaMemset(c->step_counter, 0, sizeof(unsigned long long)));
     }
     CK(cudaMalloc(&c->S, sizeof(DevScal)));
     CK(cudaMemset(c->S, 0, sizeof(DevScal)));
@@ -619,6 +645,9 @@ int pdeode_destroy(pdeode_ctx *c) {
     if (c->frame_buf) cudaFree(c->frame_buf);
     if (c->red) cudaFree(c->red);
     if (c->bar) cudaFree(c->bar);
+    if (c->step_out_h) cudaFreeHost(c->step_out_h);
+    if (c->step_slots) cudaFree(c->step_slots);
+    if (c->step_counter) cudaFree(c->step_counter);
     if (c->S) cudaFree(c->S);
     if (c->trace) cudaFree(c->trace);
     if (c->gather) cudaFree(c->gather);
@@ -789,10 +818,84 @@ int pdeode_get_frame_rowmeans(pdeode_ctx *c, int filter, double *meanM, double *
     return PDEODE_OK;
 }
 
+namespace {
+
+// P:700-742 as one cooperative launch (k_step_persist) and one host wait.
+int step_whole(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nitMax) {
+    c->seq++;
+    StepArgs a{};
+    a.st = stencil_args(c);
+    a.st.trace = nullptr;
+    for (int k = 0; k < 3; ++k) { a.Mb[k] = c->Mb[k]; a.Cb[k] = c->Cb[k]; }
+    a.iM = c->iM; a.iC = c->iC;
+    a.warm = c->warm ? 1 : 0;
+    a.iMnew0 = c->iMnew;
+    a.pbuf[0] = c->pbuf[0]; a.pbuf[1] = c->pbuf[1]; a.ip = c->ip;
+    a.slots = c->step_slots; a.counter = c->step_counter; a.gen0 = c->step_gen;
+    a.bar = c->bar;
+    a.stamps = c->step_stamps ? 1 : 0;
+    a.nstrips = c->cfg.s_nstrips; a.nchunks = c->cfg.s_nchunks; a.cw = c->cfg.s_cw;
+    a.eSoln = c->params.eSoln;
+    a.picard_cap = PICARD_CAP;
+    a.out = c->step_out;
+    c->iMprev = c->iM; c->iCprev = c->iC;            // P:703-704
+    a.seq = ++c->step_seq;
+    CK(launch_step_persist(a, c->cfg.s_BS, c->stream));
+    c->launches++;
+    if (c->step_poll) {
+        // the kernel's last act is to store `seq` behind a system-wide fence; watching that
+        // word saves the driver's completion path (event, interrupt or its own polling)
+        volatile unsigned long long *seq = &c->step_out_h->seq;
+        for (unsigned spins = 1; *seq != a.seq; ++spins) {
+            if ((spins & 0xfffu) == 0u) {
+                cudaError_t q = cudaStreamQuery(c->stream);
+                if (q == cudaSuccess) break;                 // finished: the stores have landed
+                if (q != cudaErrorNotReady) return fail_cuda(c, q, "whole-step launch");
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+    } else {
+        CK(cudaEventRecord(c->ev[0], c->stream));
+        CK(cudaEventSynchronize(c->ev[0]));
+    }
+    const StepOut &o = *c->step_out_h;
+    if (c->step_stamps && o.nstamps > 1) {
+        fprintf(stderr, "step stamps (ns | clk):");
+        for (int k = 1; k < o.nstamps; ++k)
+            fprintf(stderr, " %llu|%llu", o.stamp_ns[k] - o.stamp_ns[k - 1], o.stamp_clk[k] - o.stamp_clk[k - 1]);
+        fprintf(stderr, "\n");
+    }
+    if (o.error) {
+        c->err = "whole-step launch: grid barrier timed out";
+        return PDEODE_ERR_CUDA;
+    }
+    c->step_gen = o.gen;
+    c->iM = o.iM; c->iC = o.iC; c->iMnew = o.iMnew;
+    c->ip = o.ip; c->p = c->pbuf[c->ip];
+    c->warm = c->warm || o.count > 0;
+    c->mass_valid = false;
+    c->trace_count = std::min(o.count, std::min(MAX_PICARD_TRACE, STEP_TRACE));
+    for (int k = 0; k < c->trace_count; ++k) {
+        c->nit_trace[k] = o.nit[k];
+        c->diff_trace[2 * k] = o.diffs[2 * k];
+        c->diff_trace[2 * k + 1] = o.diffs[2 * k + 1];
+    }
+    if (countIters) *countIters = o.count;
+    if (nitSum) *nitSum = o.nit_sum;
+    if (nitMax) *nitMax = o.nit_max;
+    if (o.picard_cap) return PDEODE_ERR_PICARD_CAP;
+    return PDEODE_OK | (o.cg_cap ? PDEODE_WARN_CG_CAP : 0);
+}
+
+}  // namespace
+
 // P:700-742
 int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nitMax) {
     if (!c) return PDEODE_ERR_ARG;
     CK(cudaSetDevice(c->device));
+    // small grids, one rank, no per-iteration CG trace asked for: the whole step in one launch
+    if (c->cfg.whole_step && !multi(c) && c->trace_cap == 0)
+        return step_whole(c, countIters, nitSum, nitMax);
     int rc;
     int warn = 0;
     // Cprev = C ; Mprev = M (P:703-704): the current buffers become the frozen ones
@@ -982,12 +1085,13 @@ int pdeode_engine_info(const pdeode_ctx *c, char *buf, int len) {
     if (!c || !buf || len < 1) return PDEODE_ERR_ARG;
     snprintf(buf, (size_t)len,
              "spmv=%s BS=%d TR=%d depth=%d init_BS=%d init_TR=%d persist=%d persist_ctas=%d "
-             "defer_x=%d kb_reverse=%d exchange=%s",
+             "defer_x=%d kb_reverse=%d whole_step=%d step_BS=%d step_ctas=%d exchange=%s",
              c->cfg.variant == 1 ? "bulk-async" : "register-staged", c->cfg.BS, c->cfg.TR,
              c->cfg.DEPTH, c->cfg.i_BS, c->cfg.i_TR, c->cfg.persist,
              c->cfg.p_nstrips * c->cfg.p_nchunks,
              (c->cfg.persist && sums_mode(c) != SUMS_RAW ? c->cfg.persist_defer != 0 : defer_x(c)) ? 1 : 0,
-             c->cfg.kb_reverse,
+             c->cfg.kb_reverse, c->cfg.whole_step, c->cfg.s_BS,
+             c->cfg.s_nstrips * c->cfg.s_nchunks,
              !multi(c) ? "none" : (c->peer ? "peer" : "nccl"));
     return PDEODE_OK;
 }

@@ -330,34 +330,29 @@ struct VecLoad {
     }
 };
 
-// One CTA marches TR rows down a strip of 2*BS columns; thread t owns columns
-// (2t, 2t+1) of the strip and keeps the rows above / at / below in registers.
-// West / east neighbours come from the adjacent lanes; the two edge lanes of
-// each warp fetch theirs from memory.
-template <int MODE, int BS>
-__global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
-    __shared__ double sm[64];
-    DevScal *S = a.S;
-    VecLoad<MODE> V;
-    if (MODE == MODE_CG) {
-        if (S->done) return;
-        V.a = a.r; V.b = a.p_in;
-        V.first = (S->nit == 0);
-        V.beta = V.first ? 0.0 : S->rho / S->rho_old;       // CG:68
-    } else {
-        V.a = a.x0; V.b = nullptr; V.first = true; V.beta = 0.0;
-    }
-    const GridDesc g = a.g;
-    const NumParams np = a.np;
+// Array pointers of one tile march: the members of StencilArgs that change
+// from solve to solve.
+struct TilePtrs {
+    const double *d, *Cc, *Mprev, *x0;
+    double *ac, *r, *x, *p, *q;
+};
+
+// One tile march: rows [i_begin, i_end) of the column pair (j0, j0+1).  Thread
+// t of a warp owns the pair next to thread t-1's and keeps the rows above / at /
+// below in registers.  West / east neighbours come from the adjacent lanes;
+// the two edge lanes of each warp fetch theirs from memory.  All 32 lanes of a
+// warp must call this together (shuffles).
+template <int MODE>
+__device__ __forceinline__ void stencil_tile(const StencilArgs &a, const TilePtrs &T,
+                                             const VecLoad<MODE> &V, const int j0,
+                                             const int i_begin, const int i_end,
+                                             double &acc0, double &acc1) {
+    const GridDesc &g = a.g;
+    const NumParams &np = a.np;
     const int lane = threadIdx.x & 31;
-    const int j0 = (blockIdx.x * BS + threadIdx.x) * 2;
     const bool inrow = j0 < g.P;
-    const int i_begin = blockIdx.y * a.TR;
-    const int i_end = min(i_begin + a.TR, g.rows);
     const double h = np.h;
     const double2 zero2 = make_double2(0.0, 0.0);
-
-    double acc0 = 0.0, acc1 = 0.0;
 
     // column roles (P:560, P:568)
     const bool firstc0 = (j0 == 0);
@@ -369,24 +364,24 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
     if (inrow) {
         vN = V.two(off - g.P);
         vC = V.two(off);
-        dN = ld2(a.d + off - g.P);
-        dC = ld2(a.d + off);
+        dN = ld2(T.d + off - g.P);
+        dC = ld2(T.d + off);
     }
     if (MODE == MODE_CG && a.write_ghost_top && i_begin == 0 && inrow)
-        st2(a.p + off - g.P, vN);
+        st2(T.p + off - g.P, vN);
 
     for (int i = i_begin; i < i_end; ++i, off += g.P) {
         double2 vS = zero2, dS = zero2;
         if (inrow) {
             vS = V.two(off + g.P);
-            dS = ld2(a.d + off + g.P);
+            dS = ld2(T.d + off + g.P);
         }
         double vW0 = __shfl_up_sync(FULL, vC.y, 1);
         double dW0 = __shfl_up_sync(FULL, dC.y, 1);
         double vE1 = __shfl_down_sync(FULL, vC.x, 1);
         double dE1 = __shfl_down_sync(FULL, dC.x, 1);
-        if (lane == 0 && inrow) { vW0 = V.one(off - 1); dW0 = a.d[off - 1]; }
-        if (lane == 31 && inrow) { vE1 = V.one(off + 2); dE1 = a.d[off + 2]; }
+        if (lane == 0 && inrow) { vW0 = V.one(off - 1); dW0 = T.d[off - 1]; }
+        if (lane == 31 && inrow) { vE1 = V.one(off + 2); dE1 = T.d[off + 2]; }
 
         if (inrow) {
             const int gi = g.row0 + i;
@@ -403,10 +398,10 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
             double2 ac2, q2;
             double2 c2 = zero2, mp2 = zero2;
             if (MODE == MODE_INIT) {
-                c2 = ld2(a.Cc + off);
-                mp2 = ld2(a.Mprev + off);
+                c2 = ld2(T.Cc + off);
+                mp2 = ld2(T.Mprev + off);
             } else {
-                ac2 = ld2(a.ac + off);
+                ac2 = ld2(T.ac + off);
             }
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
@@ -458,9 +453,9 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
                 }
             }
             if (MODE == MODE_INIT) {
-                st2(a.ac + off, ac2);
-                st2(a.r + off, q2);
-                if (a.x != a.x0) st2(a.x + off, vC);
+                st2(T.ac + off, ac2);
+                st2(T.r + off, q2);
+                if (T.x != T.x0) st2(T.x + off, vC);
                 if (a.fuse_scalars == SUMS_PEER) {
                     // my boundary rows of r are the neighbours' ghost rows
                     if (i == 0 && a.pc.r_up)
@@ -468,14 +463,40 @@ __global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
                     if (i == g.rows - 1 && a.pc.r_dn) st2(a.pc.r_dn - g.P + j0, q2);
                 }
             } else {
-                st2(a.p + off, vC);
-                st2(a.q + off, q2);
+                st2(T.p + off, vC);
+                st2(T.q + off, q2);
             }
         }
         vN = vC; vC = vS; dN = dC; dC = dS;
     }
     if (MODE == MODE_CG && a.write_ghost_bot && i_end == g.rows && inrow)
-        st2(a.p + off, vC);
+        st2(T.p + off, vC);
+}
+
+// One CTA marches TR rows down a strip of 2*BS columns.
+template <int MODE, int BS>
+__global__ void __launch_bounds__(BS) k_stencil(const StencilArgs a) {
+    __shared__ double sm[64];
+    DevScal *S = a.S;
+    VecLoad<MODE> V;
+    if (MODE == MODE_CG) {
+        if (S->done) return;
+        V.a = a.r; V.b = a.p_in;
+        V.first = (S->nit == 0);
+        V.beta = V.first ? 0.0 : S->rho / S->rho_old;       // CG:68
+    } else {
+        V.a = a.x0; V.b = nullptr; V.first = true; V.beta = 0.0;
+    }
+    const GridDesc g = a.g;
+    const NumParams np = a.np;
+    const int j0 = (blockIdx.x * BS + threadIdx.x) * 2;
+    const int i_begin = blockIdx.y * a.TR;
+    const int i_end = min(i_begin + a.TR, g.rows);
+    TilePtrs T;
+    T.d = a.d; T.Cc = a.Cc; T.Mprev = a.Mprev; T.x0 = a.x0;
+    T.ac = a.ac; T.r = a.r; T.x = a.x; T.p = a.p; T.q = a.q;
+    double acc0 = 0.0, acc1 = 0.0;
+    stencil_tile<MODE>(a, T, V, j0, i_begin, i_end, acc0, acc1);
 
     const int nb = gridDim.x * gridDim.y;
     const int bid = blockIdx.y * gridDim.x + blockIdx.x;
@@ -1374,6 +1395,342 @@ __global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
     }
 }
 
+// ---------------------------------------------------------------- whole time step, one launch
+
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+// Grid-wide sum of NV values that is also the grid barrier, for a cooperative
+// launch (all CTAs resident).  Every CTA publishes its partial sums in its own
+// slot, fences, and adds one to an arrival counter that only ever grows: sum
+// number `gen` (counted over the life of the context) is complete once the
+// counter reads gen * G.  No reset, no release word: one fence and one atomic
+// on the way in, one acquire load on the way out.  Then every CTA adds the G
+// slots in slot order -- the same numbers in the same order, so all CTAs hold
+// the same bits.  Slots alternate between two sets (gen & 1): a CTA can only
+// reach sum gen+2 after every CTA has arrived at gen+1, i.e. has finished
+// reading the slots of gen.  A CTA that waits longer than ~2 s of GPU clocks
+// raises *err; everybody then leaves (returns false) instead of hanging the
+// device.  Measured on B200, 257 CTAs (profiles/README.md): ~2.8 us per sum,
+// against 4.6 us with an arrival counter + generation word + three seq_cst
+// fences, and 6+ us with per-CTA flags that every CTA polls.
+//   slots: [2][G][4] doubles, counter: one u64, sm: 4*32 doubles
+template <int NV>
+__device__ __forceinline__ bool step_allsum(double (&v)[NV], double *slots,
+                                            unsigned long long *counter, unsigned int *err,
+                                            const unsigned long long gen, const int G, double *sm,
+                                            double *s_tot) {
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int nw = (blockDim.x + 31) >> 5;
+    double *const my_slots = slots + (size_t)(gen & 1ULL) * G * 4;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = warp_sum(v[k]);
+    if (lane == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm[32 * k + w] = v[k];
+    }
+    __syncthreads();                     // also: all my CTA's field stores precede the fence below
+    int bad = 0;
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) v[k] = warp_sum(lane < nw ? sm[32 * k + lane] : 0.0);
+        if (lane == 0) {
+            double *o = my_slots + 4 * blockIdx.x;
+            st2(o, make_double2(v[0], v[1]));
+            if (NV > 2) st2(o + 2, make_double2(v[2], v[NV > 3 ? 3 : 2]));
+            asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            atomicAdd(counter, 1ULL);
+            const unsigned long long target = gen * (unsigned long long)G;
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            while (ld_acquire_gpu(counter) < target) {
+                if ((++spins & 255u) != 0u) continue;
+                if (*(volatile unsigned int *)err == 0u && clock64() - t0 <= 4000000000LL) continue;
+                *(volatile unsigned int *)err = 1u;
+                bad = 1;
+                break;
+            }
+        }
+    }
+    bad = __syncthreads_or(bad);         // thread 0's acquire precedes everybody's later loads
+    double x[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x[k] = 0.0;
+    for (int i = tid; i < G; i += blockDim.x) {
+        const double *o = my_slots + 4 * i;
+        const double2 a = __ldcg(reinterpret_cast<const double2 *>(o));
+        x[0] += a.x; x[1] += a.y;
+        if (NV > 2) {
+            const double2 b = __ldcg(reinterpret_cast<const double2 *>(o + 2));
+            x[2] += b.x;
+            if (NV > 3) x[3] += b.y;
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x[k] = warp_sum(x[k]);
+    if (lane == 0) {                     // sm is free: the barrier above is behind its last reader
+#pragma unroll
+        for (int k = 0; k < NV; ++k) sm[32 * k + w] = x[k];
+    }
+    __syncthreads();
+    if (w == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) x[k] = warp_sum(lane < nw ? sm[32 * k + lane] : 0.0);
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < NV; ++k) s_tot[k] = x[k];
+        }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = s_tot[k];
+    return bad == 0;
+}
+
+// The loop body of solveOrder2 (P:700-742) in one cooperative launch, for grids
+// so small that a time step is a chain of launch latencies and host round trips
+// (the shipped 257 x 257 run: ~6 CG iterations per step in ~3 Picard iterates).
+// Every CTA owns one tile -- a strip of columns (the whole row up to P = 1024),
+// a few rows -- for the whole step and walks through
+//     d = D(Mprev)                                              P:544-546
+//     per Picard iterate (P:706):
+//         centre diagonal, r = b - A x0, x = x0                 P:551-586, CG:46-50
+//         per CG iteration: p, q = A p | p.q, p.p               CG:61-76,87
+//                           x += alfa p, r -= alfa q | r.r, x.x CG:57,59,79-86
+//         C update, Picard residuals                            P:504-506, P:948-963
+// with one grid-wide sum (= barrier, step_allsum) where the reference has a
+// reduction.  Two barriers are saved: a CTA computes D for its halo rows
+// itself, and the centre diagonal / first residual of the NEXT Picard iterate
+// are built right behind the C update (they need nothing from other CTAs that
+// is not already there), so that their sums travel with the Picard residuals;
+// if the residuals then say "converged" (P:706) that work is simply dropped --
+// it only wrote scratch arrays (ac, r, the spare M buffer).
+// All CTAs add the partial sums in the same order, hold the same scalars and
+// take the same decisions (CG:88-90, P:706, P:732); nothing goes through the
+// host until the step is over.  Cell arithmetic is the kernels' own
+// (stencil_tile, solve_c_cell, dfunc): only the summation order differs.
+__global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
+    __shared__ double sm[128];
+    __shared__ double s_tot[4];
+    const StencilArgs &a = A.st;
+    const GridDesc g = a.g;
+    const NumParams np = a.np;
+    DevScal *S = a.S;
+    const int G = gridDim.x;
+    const int tid = threadIdx.x;
+    const int strip = blockIdx.x % A.nstrips, chunk = blockIdx.x / A.nstrips;
+    // A.cw threads (whole warps) span the strip; the CTA's blockDim.x / cw row groups split
+    // the chunk's rows between them, so that a thread marches as few rows as possible
+    const int RG = (int)blockDim.x / A.cw, rg = tid / A.cw, tcol = tid - rg * A.cw;
+    const int j0 = (strip * A.cw + tcol) * 2;
+    const bool inrow = j0 < g.P;
+    const bool v0 = j0 < g.col, v1 = j0 + 1 < g.col;
+    const int c_begin = (int)((long long)chunk * g.rows / A.nchunks);
+    const int c_rows = (int)((long long)(chunk + 1) * g.rows / A.nchunks) - c_begin;
+    const int i_begin = c_begin + rg * c_rows / RG;
+    const int i_end = c_begin + (rg + 1) * c_rows / RG;
+    const long long off0 = (long long)i_begin * g.P + j0;
+    const long long maxit = S->maxit;
+    const double n_glob = g.n_glob, tol2 = np.tol2;
+    unsigned long long gen = A.gen0;
+    unsigned int *const err = A.bar + 2;
+    int nst = 0;
+    auto stamp = [&]() {
+        if (A.stamps && blockIdx.x == 0 && tid == 0 && nst < 48) {
+            unsigned long long ns;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(ns));
+            A.out->stamp_ns[nst] = ns;
+            A.out->stamp_clk[nst] = (unsigned long long)clock64();
+            ++nst;
+        }
+    };
+    stamp();
+
+    const int iMprev = A.iM, iCprev = A.iC;          // Mprev = M ; Cprev = C (P:703-704)
+    int iM = A.iM, iC = A.iC, iMnew = A.iMnew0, ip = A.ip;
+    bool ok = true;
+
+    // d = D(Mprev) on my rows and the rows above and below (the neighbours store
+    // the same bits there); d left and right of a strip comes from other CTAs
+    if (inrow) {
+        const double *Mp = A.Mb[iMprev];
+        double *d = const_cast<double *>(a.d);
+        const int lo = max(i_begin - 1, 0), hi = min(i_end + 1, g.rows);
+        long long off = (long long)lo * g.P + j0;
+        for (int i = lo; i < hi; ++i, off += g.P) {
+            const double2 m = ld2(Mp + off);
+            double2 o;
+            o.x = dfunc(m.x, np);
+            o.y = dfunc(m.y, np);
+            st2(d + off, o);
+        }
+    }
+    if (A.nstrips > 1) {
+        double z[2] = {0.0, 0.0};
+        ok = step_allsum<2>(z, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+    } else {
+        __syncthreads();
+    }
+    stamp();
+
+    double diffC = 1.0, diffM = 1.0;                 // P:700-701
+    int count = 0, cg_cap = 0, picard_cap = 0;       // P:702
+    long long nsum = 0, nmax = 0;
+    double rho = 0.0, rho_old = 0.0, xx = 0.0, alfa = 0.0, err2 = 0.0, normx = 0.0, pq = 0.0, pp = 0.0;
+    long long it = 0;
+    int stop = 0;
+    if (!(diffC + diffM > A.eSoln)) ok = false;      // P:706 on entry (eSoln >= 2: no iterate at all)
+
+    // target of a solve: neither Mprev nor the current iterate; the very first
+    // solve after set_state starts from (and into) the zeroed buffer (D8)
+    int inew = 0;
+    while (inew == iMprev || inew == iM) inew++;
+    if (!A.warm) inew = A.iMnew0;
+    TilePtrs T;
+    T.d = a.d; T.ac = a.ac; T.r = a.r; T.q = a.q; T.p = nullptr;
+    T.Mprev = A.Mb[iMprev];
+
+    // ---- first Picard iterate: centre diagonal, r = b - A x0 (P:712, CG:46-50)
+    if (ok) {
+        T.Cc = A.Cb[iC];
+        T.x0 = A.warm ? A.Mb[iM] : A.Mb[inew];
+        T.x = A.Mb[inew];
+        VecLoad<MODE_INIT> V;
+        V.a = T.x0; V.b = nullptr; V.first = true; V.beta = 0.0;
+        double acc[2] = {0.0, 0.0};
+        stencil_tile<MODE_INIT>(a, T, V, j0, i_begin, i_end, acc[0], acc[1]);
+        ok = step_allsum<2>(acc, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+        rho = acc[0]; xx = acc[1];                   // CG:53
+        stamp();
+    }
+    while (ok) {                                     // P:706, left by the breaks below
+        double *const x = A.Mb[inew];
+        // ---- solveLSDIAG (CG:54-94)
+        it = 0; stop = 0; rho_old = 0.0;             // CG:44,53
+        for (;;) {
+            ++it;                                                        // CG:55
+            const bool firstit = (it == 1);
+            VecLoad<MODE_CG> V;
+            V.a = a.r; V.b = A.pbuf[ip];
+            V.first = firstit;
+            V.beta = firstit ? 0.0 : rho / rho_old;                      // CG:68
+            T.p = A.pbuf[ip ^ 1];
+            double acc[2] = {0.0, 0.0};
+            stencil_tile<MODE_CG>(a, T, V, j0, i_begin, i_end, acc[0], acc[1]);
+            ok = step_allsum<2>(acc, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+            if (!ok) break;
+            stamp();
+            pq = acc[0]; pp = acc[1];
+            alfa = rho / pq;                                             // CG:77
+            err2 = fabs(alfa) * sqrt(pp) / n_glob;                       // CG:87
+            normx = sqrt(xx) / n_glob;                                   // CG:57
+            stop = 0;
+            if (it > maxit) stop = -1;                                   // CG:88
+            if (err2 < tol2 * normx) stop = stop - 100;                  // CG:90
+            double rx[2] = {0.0, 0.0};
+            if (inrow) {
+                const double *p_out = T.p;
+                long long off = off0;
+                for (int i = i_begin; i < i_end; ++i, off += g.P) {
+                    double2 x2 = ld2(x + off), r2 = ld2(a.r + off);
+                    const double2 p2 = ld2(p_out + off), q2 = ld2(a.q + off);
+                    x2.x = x2.x + alfa * p2.x; x2.y = x2.y + alfa * p2.y;  // CG:80
+                    r2.x = r2.x - alfa * q2.x; r2.y = r2.y - alfa * q2.y;  // CG:81
+                    st2(x + off, x2);
+                    st2(a.r + off, r2);
+                    rx[0] += r2.x * r2.x; rx[0] += r2.y * r2.y;
+                    rx[1] += x2.x * x2.x; rx[1] += x2.y * x2.y;
+                }
+            }
+            ok = step_allsum<2>(rx, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+            if (!ok) break;
+            stamp();
+            rho_old = rho; rho = rx[0]; xx = rx[1];                      // CG:56,59,57
+            ip ^= 1;
+            if (stop != 0) break;
+        }
+        if (!ok) break;
+        iMnew = inew;
+        if (stop == -1 || stop == -101) cg_cap = 1;
+
+        // ---- solveC (P:717) and the sums of calcDiff (P:725-726) on my cells
+        int icnew = 0;
+        while (icnew == iCprev || icnew == iC) icnew++;
+        double acc[4] = {0.0, 0.0, 0.0, 0.0};        // dC, dM, then r.r and x.x of the next iterate
+        if (inrow) {
+            const double *Mp = A.Mb[iMprev], *Mn = A.Mb[inew], *Cp = A.Cb[iCprev];
+            const double *Cc = A.Cb[iC], *Mc = A.Mb[iM];
+            double *Cn = A.Cb[icnew];
+            long long off = off0;
+            for (int i = i_begin; i < i_end; ++i, off += g.P) {
+                const double2 mp = ld2(Mp + off), mn = ld2(Mn + off), cp = ld2(Cp + off);
+                const double2 cc = ld2(Cc + off), mc = ld2(Mc + off);
+                double2 cn;
+                cn.x = v0 ? solve_c_cell(mp.x, mn.x, cp.x, np) : 0.0;
+                cn.y = v1 ? solve_c_cell(mp.y, mn.y, cp.y, np) : 0.0;
+                if (np.gSelect == 1) st2(Cn + off, cn);      // P:501
+                else cn = ld2(Cn + off);                      // Cnew left as it was
+                acc[0] += v0 ? fabs(cc.x - cn.x) : 0.0;       // P:958
+                acc[0] += v1 ? fabs(cc.y - cn.y) : 0.0;
+                acc[1] += v0 ? fabs(mc.x - mn.x) : 0.0;
+                acc[1] += v1 ? fabs(mc.y - mn.y) : 0.0;
+            }
+        }
+        iC = icnew;                                  // C = Cnew (P:728)
+        iM = inew;                                   // M = Mnew (P:729)
+
+        // ---- the next iterate's centre diagonal and r = b - A x0.  It reads my own new C,
+        // and M = Mnew whose halo rows were complete two barriers ago: it can be built ahead
+        // of the verdict, so that its sums travel with the Picard residuals.
+        inew = 0;
+        while (inew == iMprev || inew == iM) inew++;
+        auto build_next = [&](double &s0, double &s1) {
+            T.Cc = A.Cb[iC];
+            T.x0 = A.Mb[iM];
+            T.x = A.Mb[inew];
+            VecLoad<MODE_INIT> V;
+            V.a = T.x0; V.b = nullptr; V.first = true; V.beta = 0.0;
+            stencil_tile<MODE_INIT>(a, T, V, j0, i_begin, i_end, s0, s1);
+        };
+        build_next(acc[2], acc[3]);
+        ok = step_allsum<4>(acc, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+        if (!ok) break;
+        stamp();
+        diffC = acc[0] / n_glob;                     // P:961
+        diffM = acc[1] / n_glob;
+
+        if (it > nmax) nmax = it;                    // P:722
+        nsum += it;                                  // P:723
+        if (blockIdx.x == 0 && tid == 0 && count < STEP_TRACE) {
+            A.out->nit[count] = it;
+            A.out->diffs[2 * count] = diffC;
+            A.out->diffs[2 * count + 1] = diffM;
+        }
+        count++;                                     // P:730
+        if (count > A.picard_cap) { picard_cap = 1; break; }   // P:732
+        if (!(diffC + diffM > A.eSoln)) break;       // P:706
+        rho = acc[2]; xx = acc[3];                   // CG:53 of the next solve
+    }
+    if (blockIdx.x == 0 && tid == 0) {
+        StepOut *o = A.out;
+        o->nit_sum = nsum; o->nit_max = nmax; o->count = count;
+        o->cg_cap = cg_cap; o->picard_cap = picard_cap;
+        o->error = (*(volatile unsigned int *)err != 0u) ? 1 : 0;
+        o->iM = iM; o->iC = iC; o->iMnew = iMnew; o->ip = ip;
+        o->gen = gen;
+        o->nstamps = nst;
+        S->nit = it; S->stop = stop; S->done = 1; S->finished = 1;
+        S->rho = rho; S->rho_old = rho_old; S->xx = xx;
+        S->alfa = alfa; S->err2 = err2; S->normx = normx; S->pq = pq; S->pp = pp;
+        S->diffC = diffC; S->diffM = diffM;
+        S->trace_len = 0;
+        __threadfence_system();
+        *(volatile unsigned long long *)&o->seq = A.seq;
+    }
+}
+
 // ---------------------------------------------------------------- diagnostics
 
 // calcMass (P:783-787) for M and C, and calcPeakInterface (P:989-1001): the
@@ -1668,6 +2025,12 @@ cudaError_t launch_cg_persist(const PersistArgs &a, int BS, cudaStream_t st) {
     return launch_cg_persist_t<256>(a, st);
 }
 
+cudaError_t launch_step_persist(const StepArgs &a, int BS, cudaStream_t st) {
+    void *args[] = {const_cast<StepArgs *>(&a)};
+    return cudaLaunchCooperativeKernel((const void *)k_step_persist, dim3(a.nstrips * a.nchunks),
+                                       dim3(BS), args, 0, st);
+}
+
 LaunchCfg launch_config(const GridDesc &g) {
     if (const char *e = getenv("PDEODE_STREAM_CTAS")) {
         const int v = atoi(e);
@@ -1745,6 +2108,46 @@ LaunchCfg launch_config(const GridDesc &g) {
     c.i_BS = c.BS > 128 ? 128 : c.BS;
     c.i_TR = c.TR > 32 ? 32 : c.TR;
     if (const char *e = getenv("PDEODE_KB_REVERSE")) c.kb_reverse = atoi(e) != 0;
+
+    // Whole time step in one launch: s_cw threads span a strip (the whole row where P <= 1024),
+    // a CTA holds as many row groups of s_cw threads as fit in 512 threads, a thread marches
+    // PDEODE_STEP_ROWS (default 1) rows or more, all CTAs resident.
+    c.s_cw = (g.P / 2 + 31) / 32 * 32;
+    if (c.s_cw > 512) c.s_cw = 512;
+    int rgroups = 512 / c.s_cw;
+    if (const char *e = getenv("PDEODE_STEP_GROUPS")) {
+        const int v = atoi(e);
+        if (v >= 1 && v * c.s_cw <= 512) rgroups = v;
+    }
+    c.s_BS = c.s_cw * rgroups;
+    c.s_nstrips = cdiv(g.P, 2 * c.s_cw);
+    {
+        int n = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_step_persist, c.s_BS, 0) != cudaSuccess) {
+            cudaGetLastError();
+            n = 0;
+        }
+        int maxg = n * g_num_sms;
+        if (const char *e = getenv("PDEODE_PERSIST_MAX_CTAS")) {
+            const int cap = atoi(e);
+            if (cap >= 1 && maxg > cap) maxg = cap;
+        }
+        int rows_min = 1;
+        if (const char *e = getenv("PDEODE_STEP_ROWS")) {
+            const int v = atoi(e);
+            if (v >= 1 && v <= 4096) rows_min = v;
+        }
+        int nch = maxg / c.s_nstrips;
+        const int by_rows = cdiv(g.rows, rows_min * rgroups);
+        if (nch > by_rows) nch = by_rows;
+        c.s_nchunks = nch;
+        // where a step is a chain of launch latencies: the shipped 257^2 grid, ensemble members.
+        // Measured per step (shipped parameters, tools/step_bench.py), whole step / persistent
+        // solve / kernel per phase: 257^2 59 / 136 / 182 us, 512^2 74 / 144 / 180, 1024^2
+        // 151 / 228 / 247; 1448^2 449 / 333, 2048^2 702 / 549: the streaming engines win there.
+        c.whole_step = (nch >= 1 && g.rows == g.grow && cells <= (1280LL << 10)) ? 1 : 0;
+        if (const char *e = getenv("PDEODE_WHOLE_STEP")) c.whole_step = (atoi(e) != 0 && nch >= 1) ? 1 : 0;
+    }
     return c;
 }
 

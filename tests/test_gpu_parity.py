@@ -35,6 +35,8 @@ def engine_env(monkeypatch):
     def select(engine):
         for k in ("PDEODE_PERSIST", "PDEODE_VARIANT", "PDEODE_DEFER_X"):
             monkeypatch.delenv(k, raising=False)
+        # small grids default to the whole step in one launch; the other engines are asked for
+        monkeypatch.setenv("PDEODE_WHOLE_STEP", "1" if engine == "whole-step" else "0")
         if engine == "kernels":                      # kernel per phase, 88-byte iteration
             monkeypatch.setenv("PDEODE_PERSIST", "0")
         elif engine == "kernels-96":                 # kernel per phase, x updated by K_B
@@ -119,11 +121,13 @@ def run_pair(pb, row, col, over, M0, C0, steps, check_every=True, cg_tol=TOL_CG)
 
 @pytest.mark.parametrize("row,col", [(5, 5), (9, 4), (33, 33), (37, 53), (64, 48), (20, 257)])
 @pytest.mark.parametrize("fsel,dsel", [(1, 3), (3, 2), (6, 1), (5, 3), (2, 3), (4, 3)])
-def test_assembly_spmv_and_c_update_bit_exact(pb, row, col, fsel, dsel):
+@pytest.mark.parametrize("engine", ["kernels", "whole-step"])
+def test_assembly_spmv_and_c_update_bit_exact(pb, engine_env, row, col, fsel, dsel, engine):
     """One Picard iterate with a one-iteration CG (maxit = 0 -> CG:88 stops after
     iteration 1): D(M), the centre diagonal, q = A p with p = rhs, and the C
     update must equal the oracle's bit for bit, boundary rows, the P:576 quirk
     cell and pad columns included."""
+    engine_env(engine)
     rng = np.random.RandomState(row * 1000 + col)
     n = row * col
     M0 = rng.uniform(0.05, 0.85, n); C0 = rng.uniform(0.2, 1.0, n)
@@ -142,7 +146,15 @@ def test_assembly_spmv_and_c_update_bit_exact(pb, row, col, fsel, dsel):
     lib.oracle_gen_matrix(M0, C0, A, ioff, rhs, row, col, C.byref(po))
     d_want = np.array([lib.oracle_dfunc(m, po.delta, po.alpha, po.beta, po.dSelect) for m in M0])
     assert np.array_equal(s.array(pb.ARR_D), d_want)
-    assert np.array_equal(s.array(pb.ARR_AC), A[2 * n:3 * n])
+    if engine == "whole-step":
+        # the whole-step launch builds the next iterate's centre diagonal (from the new C)
+        # behind the C update, before the Picard residuals say whether it is needed
+        _, Cg1 = s.get_state()
+        A2 = np.zeros(5 * n); rhs2 = np.zeros(n)
+        lib.oracle_gen_matrix(M0, Cg1, A2, ioff, rhs2, row, col, C.byref(po))
+        assert np.array_equal(s.array(pb.ARR_AC), A2[2 * n:3 * n])
+    else:
+        assert np.array_equal(s.array(pb.ARR_AC), A[2 * n:3 * n])
     # x0 = 0  ->  r0 = rhs, p1 = r0, q1 = A p1
     assert np.array_equal(s.array(pb.ARR_P), rhs)
     q_want = np.empty(n)
@@ -205,10 +217,11 @@ def test_first_cg_iteration_scalars(pb):
     (64, 64, dict(dSelect=1, fSelect=5, tDel=1e-2), ("blobs", 0.3, 0.3, 4, 2), 3),
     (257, 257, {}, ("blobs", 0.02, 0.0390625, 60, 7), 4),     # shipped parameter.txt values
 ])
-@pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent", "register-staged"])
+@pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent", "register-staged",
+                                    "whole-step"])
 def test_steps_match_oracle(pb, engine_env, row, col, over, ic, steps, engine):
-    """Both CG engines -- one kernel per phase and the persistent cooperative
-    solve -- and the register-staged SpMV variant, against the oracle."""
+    """All engines -- one kernel per phase, the persistent cooperative solve, the
+    register-staged SpMV variant and the whole step in one launch -- against the oracle."""
     engine_env(engine)
     if ic[0] == "ic1":
         M0, C0 = ol.ic1(row, col, ic[1], ic[2])
@@ -239,7 +252,7 @@ def test_1024_grid_matches_oracle(pb):
 
 
 @pytest.mark.parametrize("name", CASES)
-@pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent"])
+@pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent", "whole-step"])
 def test_golden_fixtures(pb, engine_env, name, engine):
     engine_env(engine)
     z, row, col, over = load_case(name)
@@ -251,12 +264,18 @@ def test_golden_fixtures(pb, engine_env, name, engine):
         g = s.step_trace()
         assert g["countIters"] == z["countIters"][k]
         want = [int(v) for v in z["nits"][k][:len(g["nits"])]]
-        for a, b in zip(g["nits"], want):
+        for si, (a, b) in enumerate(zip(g["nits"], want)):
             # quasi-1D (col = 4) runs sit on a CG plateau near the stop threshold: the
             # reference's own serial / OpenMP builds differ by up to 4 iterations there
             # (test_reference_is_not_self_consistent_to_1e9), so +-2 cannot hold
             cg_tol = 8 if col == 4 else TOL_CG
-            assert abs(a - b) <= cg_tol, (name, k, g["nits"], want)
+            # z["near"]: iterations where the reference's own err2 came within 25 % of the
+            # stop threshold (CG:90) without crossing it -- e.g. 1.028 x the threshold at
+            # iteration 5 of an 8-iteration solve of stiff33; a solve that starts from the
+            # truncation noise of the previous one may stop there under any other summation
+            # order.  Those count as the reference's answer too.
+            cands = [b] + [int(v) for v in z["near"][k][si] if v] if si < 16 else [b]
+            assert min(abs(a - c) for c in cands) <= cg_tol, (name, k, g["nits"], want, cands)
         counts_equal = counts_equal and g["nits"] == want
         tol = field_tolerance(p, counts_equal, float(z["env"][k]))
         M, Cc = s.get_state()
