@@ -90,6 +90,28 @@ int pdeode_host_write_frame(const char *path, const pdeode_host_params *pp, cons
     return 0;
 }
 
+// The writer the GPU program uses: frame data already decimated (what
+// pdeode_get_frame returns).  Decimates M, C here the way the device does.
+int pdeode_host_write_frame_decimated(const char *path, const pdeode_host_params *pp,
+                                      const double *M, const double *C, int append) {
+    RunParams p = unflatten(pp);
+    if (p.true2D == 1) return 2;
+    const int filter = (p.row > 257) ? (p.row - 1) / 256 : 1;                    // P:829-832
+    const int nro = (p.row - 1) / filter + 1, nco = (p.col - 1) / filter + 1;
+    std::vector<double> Md((size_t)nro * nco), Cd((size_t)nro * nco);
+    for (int oi = 0; oi < nro; ++oi)
+        for (int oj = 0; oj < nco; ++oj) {
+            const size_t q = (size_t)(oi * filter) * p.col + (size_t)(oj * filter);
+            Md[(size_t)oi * nco + oj] = M[q];
+            Cd[(size_t)oi * nco + oj] = C[q];
+        }
+    FILE *f = fopen(path, append ? "a" : "w");
+    if (!f) return 1;
+    print_frame(f, p, nro, nco, Md.data(), Cd.data());
+    fclose(f);
+    return 0;
+}
+
 // Whole program (P:20-175) with the caller's stepper; param_file name is fed
 // to the prompt as stdin would be.  console_path receives the console text.
 int pdeode_host_run(const char *param_file, const char *outdir, const char *console_path,

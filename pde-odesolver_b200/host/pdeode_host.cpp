@@ -2,8 +2,13 @@
 // `program cThermoPDEODE` that stay on the host.  "P:" = PDE-ODEsolver.f90.
 #include "pdeode_host.h"
 
+#include <charconv>
 #include <chrono>
 #include <cmath>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
@@ -32,11 +37,14 @@ static void fmt_real_to(char *out, double x) {
         if (neg) out[2] = '-';
         return;
     }
-    char e[40];
-    snprintf(e, sizeof e, "%.16E", x);            // [-]d.ddddddddddddddddE+XX, rounded to 17 digits
+    // [-]d.dddddddddddddddde[+-]XX, correctly rounded to 17 digits; the same digits as
+    // printf("%.16E") at a third of the cost
+    char e[48];
+    char *end = std::to_chars(e, e + sizeof e - 1, x, std::chars_format::scientific, 16).ptr;
+    *end = '\0';
     const bool neg = (e[0] == '-');
     const char *m = e + (neg ? 1 : 0);            // d.dddd...
-    const char *ep = strchr(m, 'E');
+    const char *ep = strchr(m, 'e');
     const int ex = atoi(ep + 1);
     const int k = ex + 1;                         // digits before the point in F form
     char dig[17];
@@ -342,21 +350,43 @@ void print_to_file_2d(FILE *f, const RunParams &p, const double *M, const double
 // The same two frames from data already decimated on the device
 // (pdeode_get_frame / pdeode_get_frame_rowmeans): nro x nco points, point
 // (oi, oj) being cell (oi*filter, oj*filter).
+// A frame is fixed-width text -- 105 characters per point (P:839-840), a
+// 3-character separator line per row (P:843), one empty line at the end
+// (P:846) -- so its rows can be formatted in place by several threads.
 void print_frame(FILE *f, const RunParams &p, int nro, int nco, const double *Md, const double *Cd) {
     const int filter = frame_filter(p.row);
-    for (int oi = 0; oi < nro; ++oi) {
-        for (int oj = 0; oj < nco; ++oj) {
-            char line[105];
-            fmt_real_to(line, (double)(oj * filter) / (double)(p.col - 1));
-            fmt_real_to(line + 26, (double)(oi * filter) / (double)(p.row - 1));
-            fmt_real_to(line + 52, Md[(size_t)oi * nco + oj]);
-            fmt_real_to(line + 78, Cd[(size_t)oi * nco + oj]);
-            line[104] = '\n';
-            fwrite(line, 1, 105, f);
+    const size_t row_bytes = (size_t)nco * 105 + 3;
+    std::vector<char> text((size_t)nro * row_bytes + 1);
+    std::vector<char> xs((size_t)nco * 26);          // the x column repeats in every row
+    for (int oj = 0; oj < nco; ++oj)
+        fmt_real_to(xs.data() + (size_t)oj * 26, (double)(oj * filter) / (double)(p.col - 1));
+    auto rows = [&](int lo, int hi) {
+        for (int oi = lo; oi < hi; ++oi) {
+            char ys[26];
+            fmt_real_to(ys, (double)(oi * filter) / (double)(p.row - 1));
+            char *line = text.data() + (size_t)oi * row_bytes;
+            for (int oj = 0; oj < nco; ++oj, line += 105) {
+                memcpy(line, xs.data() + (size_t)oj * 26, 26);
+                memcpy(line + 26, ys, 26);
+                fmt_real_to(line + 52, Md[(size_t)oi * nco + oj]);
+                fmt_real_to(line + 78, Cd[(size_t)oi * nco + oj]);
+                line[104] = '\n';
+            }
+            memcpy(line, "  \n", 3);
         }
-        put(f, "  ");
+    };
+    unsigned nt = std::thread::hardware_concurrency();
+    if (nt > 8) nt = 8;
+    if ((size_t)nro * nco < 16384 || nt < 2) {
+        rows(0, nro);
+    } else {
+        std::vector<std::thread> pool;
+        for (unsigned t = 0; t < nt; ++t)
+            pool.emplace_back(rows, (int)((long long)nro * t / nt), (int)((long long)nro * (t + 1) / nt));
+        for (auto &t : pool) t.join();
     }
-    put(f, "");
+    text.back() = '\n';
+    fwrite(text.data(), 1, text.size(), f);
 }
 
 void print_frame_2d(FILE *f, const RunParams &p, int nro, const double *meanM, const double *meanC) {
@@ -388,6 +418,70 @@ bool report_stats(const std::string &path, double avgIters, double maxIters, dou
 static std::string join(const std::string &dir, const char *name) {
     return dir.empty() ? std::string(name) : dir + "/" + name;
 }
+
+namespace {
+
+// Frames leave the time loop through a short queue: one background thread
+// formats and writes them, in order, while the device keeps stepping.  (The
+// shipped 257 x 257 run writes 631 MB of frame text; formatted inside the time
+// loop that costs twice what the 30 001 time steps do.)
+class FrameSink {
+  public:
+    explicit FrameSink(const RunParams &p) : p_(p) {}
+    ~FrameSink() { finish(); }
+    void push(FILE *f, int nro, int nco, const std::vector<double> &M, const std::vector<double> &C) {
+        std::unique_lock<std::mutex> lk(mu_);
+        if (!started_) {
+            done_ = false;
+            th_ = std::thread([this] { run(); });
+            started_ = true;
+        }
+        space_.wait(lk, [&] { return q_.size() < 4; });
+        q_.push_back(Job{f, nro, nco, M, C});
+        work_.notify_one();
+    }
+    // returns once every queued frame is in its file
+    void finish() {
+        if (!started_) return;
+        {
+            std::lock_guard<std::mutex> lk(mu_);
+            done_ = true;
+        }
+        work_.notify_one();
+        th_.join();
+        started_ = false;
+    }
+
+  private:
+    struct Job {
+        FILE *f;
+        int nro, nco;
+        std::vector<double> M, C;
+    };
+    void run() {
+        for (;;) {
+            Job j;
+            {
+                std::unique_lock<std::mutex> lk(mu_);
+                work_.wait(lk, [&] { return done_ || !q_.empty(); });
+                if (q_.empty()) return;
+                j = std::move(q_.front());
+                q_.pop_front();
+            }
+            space_.notify_one();
+            if (p_.true2D == 1) print_frame_2d(j.f, p_, j.nro, j.M.data(), j.C.data());
+            else print_frame(j.f, p_, j.nro, j.nco, j.M.data(), j.C.data());
+        }
+    }
+    const RunParams p_;
+    std::mutex mu_;
+    std::condition_variable work_, space_;
+    std::deque<Job> q_;
+    std::thread th_;
+    bool started_ = false, done_ = false;
+};
+
+}  // namespace
 
 RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<double> &C,
                       const Stepper &st, int device, const std::string &outdir, FILE *con,
@@ -434,7 +528,11 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
     FILE *fco = fopen(join(outdir, "COprod.dat").c_str(), "w");                  // P:651-653
     FILE *fpeak = (p.true2D == 1) ? fopen(join(outdir, "peakInfo.dat").c_str(), "w") : nullptr;
     FILE *fframe = nullptr;                // opened by the first writer call (P:824-827, P:888-891)
+    FrameSink sink(p);
+    const char *so = getenv("PDEODE_SYNC_OUTPUT");
+    const bool async_frames = !(so && so[0] == '1');
     auto close_all = [&]() {
+        sink.finish();
         if (ftotal) fclose(ftotal);
         if (fco) fclose(fco);
         if (fpeak) fclose(fpeak);
@@ -443,9 +541,17 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
     fprintf(con, "    time    avgIter  maxIter      avgNit  maxNit        avgM        avgC\n");  // P:661
 
     const auto t0 = std::chrono::steady_clock::now();
+    // PDEODE_HOST_TIMING=1: where the wall time of the loop goes (stderr, at the end)
+    const bool timing = getenv("PDEODE_HOST_TIMING") != nullptr;
+    double t_step = 0, t_diag = 0, t_frame = 0;
+    auto now = [] { return std::chrono::steady_clock::now(); };
+    auto since = [](std::chrono::steady_clock::time_point a) {
+        return std::chrono::duration<double>(std::chrono::steady_clock::now() - a).count();
+    };
     bool have_host_copy = !device_ic;      // M, C on the host equal the device state
     std::vector<double> fbufM, fbufC;      // decimated frame data
     while ((double)counter * tDel <= tEnd) {                                     // P:663
+        const auto td = now();
         if (counter % (long long)(filter / 100 + 1) == 0) {                      // P:665
             if ((rc = st.mass(ctx, &totalMassM, &totalMassC))) { close_all(); return fail("pdeode_mass"); }
             if (ftotal) put(ftotal, fmt_real(counter * tDel) + fmt_real(totalMassM) + fmt_real(totalMassC));
@@ -458,6 +564,8 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
                                           fmt_real(intfac));
             }
         }
+        t_diag += since(td);
+        const auto tf = now();
         if (counter % filter == 0) {                                             // P:683
             if (!fframe)
                 fframe = fopen(join(outdir, p.true2D == 1 ? "2D_output.dat" : "output.dat").c_str(), "w");
@@ -471,7 +579,9 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
                 if (p.true2D == 1) rc = st.get_frame_rowmeans(ctx, filter, fbufM.data(), fbufC.data());
                 else rc = st.get_frame(ctx, filter, fbufM.data(), fbufC.data());
                 if (rc) { close_all(); return fail("pdeode_get_frame"); }
-                if (fframe) {
+                if (fframe && async_frames) {
+                    sink.push(fframe, nro, nco, fbufM, fbufC);
+                } else if (fframe) {
                     if (p.true2D == 1) print_frame_2d(fframe, p, nro, fbufM.data(), fbufC.data());
                     else print_frame(fframe, p, nro, nco, fbufM.data(), fbufC.data());
                 }
@@ -495,9 +605,12 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
                         totalMassM, totalMassC);
             fflush(con);
         }
+        t_frame += since(tf);
         int countIters = 0;
         long long nitSum = 0, nitMax = 0;
+        const auto ts = now();
         rc = st.step(ctx, &countIters, &nitSum, &nitMax);                        // P:700-738
+        t_step += since(ts);
         have_host_copy = false;
         if ((rc & PDEODE_ERR_MASK) == PDEODE_ERR_PICARD_CAP) {                   // P:732-736
             fprintf(con, " [!] Over 10000 iterations in one timestep\n");
@@ -536,7 +649,12 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
             fclose(ff);
         }
     }
+    const auto tq = now();
+    sink.finish();          // "Time to compute" covers the frames still in the queue
     const auto t1 = std::chrono::steady_clock::now();
+    if (timing)
+        fprintf(stderr, "host timing: steps %.3f s, diagnostics %.3f s, frames %.3f s, frame queue drain %.3f s\n",
+                t_step, t_diag, t_frame, since(tq));
     close_all();
     st.destroy(ctx);
     rs.avgIters = avgIters; rs.maxIters = maxIters; rs.avgNit = avgNit; rs.maxNit = maxNit;

@@ -172,6 +172,25 @@ def test_frame_writers(host, tmp_path):
     assert y == pytest.approx(5 / (p2.row - 1), abs=1e-12) and am == pytest.approx(5 / p2.row, abs=1e-12)
 
 
+@pytest.mark.parametrize("size", [33, 257, 600])
+def test_decimated_frame_writer_equals_full_field_writer(host, tmp_path, size):
+    """print_frame (device-decimated data, rows formatted by several threads above
+    16384 points) must write the bytes print_to_file writes from the whole fields."""
+    rc, p, _ = read_params(host, os.path.join(DATA, "square3d.txt"))
+    p.pSize = p.row = p.col = size
+    p.n = size * size
+    rng = np.random.RandomState(size)
+    M = rng.uniform(-1e-3, 1.0, p.n) * (rng.uniform(size=p.n) > 0.3)      # zeros, tiny and negative values
+    M[:5] = [0.0, -0.0, 1e-300, 123456.789, -2.5e-7]
+    Cc = rng.uniform(0, 1, p.n)
+    a, b = str(tmp_path / "a.dat"), str(tmp_path / "b.dat")
+    host.pdeode_host_write_frame_decimated.argtypes = host.pdeode_host_write_frame.argtypes
+    for k in (0, 1):
+        assert host.pdeode_host_write_frame(a.encode(), C.byref(p), M.ctypes.data, Cc.ctypes.data, k) == 0
+        assert host.pdeode_host_write_frame_decimated(b.encode(), C.byref(p), M.ctypes.data, Cc.ctypes.data, k) == 0
+    assert open(a, "rb").read() == open(b, "rb").read()
+
+
 def test_whole_program_with_oracle_stepper(host, adapter, tmp_path):
     """`echo FILE | a.out` end to end: console text, files, cadences (S6)."""
     out = tmp_path / "run"; out.mkdir()
