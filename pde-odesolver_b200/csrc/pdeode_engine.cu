@@ -12,6 +12,7 @@
 
 #include <algorithm>
 #include <atomic>
+#include <sched.h>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -58,6 +59,7 @@ struct pdeode_ctx {
     StepOut *step_out_h = nullptr;    // whole-step launch: its report, mapped host memory
     StepOut *step_out = nullptr;      // the same, device-side address
     bool step_poll = true;            // wait for the report by watching its sequence word
+    bool step_yield = false;          // PDEODE_STEP_YIELD=1: give the core away between looks (ensembles)
     bool step_stamps = false;         // PDEODE_STEP_STAMPS=1: print CTA 0's phase times of every step to stderr
     unsigned long long step_seq = 0;
     double *step_slots = nullptr;     // whole-step launch: partial sums and arrival counter of its grid-wide sums
@@ -555,6 +557,8 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
         CK(cudaHostGetDevicePointer(&c->step_out, c->step_out_h, 0));
         const char *pe = getenv("PDEODE_STEP_POLL");
         c->step_poll = !(pe && pe[0] == '0');
+        const char *sh = getenv("PDEODE_STEP_YIELD");
+        c->step_yield = sh && sh[0] == '1';
         const char *se = getenv("PDEODE_STEP_STAMPS");
         c->step_stamps = se && se[0] == '1';
         const size_t G = (size_t)c->cfg.s_nstrips * c->cfg.s_nchunks;
@@ -847,6 +851,7 @@ int step_whole(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nit
         // word saves the driver's completion path (event, interrupt or its own polling)
         volatile unsigned long long *seq = &c->step_out_h->seq;
         for (unsigned spins = 1; *seq != a.seq; ++spins) {
+            if (c->step_yield && (spins & 0x3fu) == 0u) sched_yield();   // members of an ensemble share the cores
             if ((spins & 0xfffu) == 0u) {
                 cudaError_t q = cudaStreamQuery(c->stream);
                 if (q == cudaSuccess) break;                 // finished: the stores have landed

@@ -2080,7 +2080,11 @@ LaunchCfg launch_config(const GridDesc &g) {
     int nch = per_sm * g_num_sms / c.p_nstrips;
     const int by_rows = g.rows / 4 > 0 ? g.rows / 4 : 1;
     if (nch > by_rows) nch = by_rows;
-    // several contexts sharing one GPU (ensembles): leave room for the others' grids
+    // several contexts sharing one GPU (ensembles): leave room for the others' grids --
+    // PDEODE_GPU_SHARE=n takes 1/n of the resident CTAs, PDEODE_PERSIST_MAX_CTAS caps them
+    int share = 1;
+    if (const char *e = getenv("PDEODE_GPU_SHARE")) share = atoi(e) > 1 ? atoi(e) : 1;
+    if (share > 1) nch = nch / share > 0 ? nch / share : 1;
     if (const char *e = getenv("PDEODE_PERSIST_MAX_CTAS")) {
         const int cap = atoi(e) / c.p_nstrips;
         if (cap >= 1 && nch > cap) nch = cap;
@@ -2128,6 +2132,7 @@ LaunchCfg launch_config(const GridDesc &g) {
             n = 0;
         }
         int maxg = n * g_num_sms;
+        if (share > 1) maxg = maxg / share > c.s_nstrips ? maxg / share : c.s_nstrips;
         if (const char *e = getenv("PDEODE_PERSIST_MAX_CTAS")) {
             const int cap = atoi(e);
             if (cap >= 1 && maxg > cap) maxg = cap;

@@ -12,7 +12,7 @@
 // DIRNAME (runAll.sh:3-4); the console goes to <name>Output/console.txt.
 // Members are replicas: no communication between them.  They are dealt
 // round-robin over the visible GPUs (PDEODE_DEVICES = "0,1,..." to restrict)
-// and PDEODE_MEMBERS_PER_GPU (default 8) of them run concurrently per GPU,
+// and PDEODE_MEMBERS_PER_GPU (default 16) of them run concurrently per GPU,
 // each on its own context and stream, so that small grids fill the device.
 #include <algorithm>
 #include <atomic>
@@ -57,16 +57,18 @@ int main(int argc, char **argv) {
         }
         for (int i = 0; i < n; ++i) devices.push_back(i);
     }
-    int per_gpu = 8;     // measured best for 512^2 members on a B200 (profiles/README.md)
+    int per_gpu = 16;    // measured best for 512^2 members on a B200 (profiles/README.md)
     if (const char *m = getenv("PDEODE_MEMBERS_PER_GPU")) per_gpu = atoi(m) > 0 ? atoi(m) : 1;
 
-    // members share a GPU: each persistent solve takes its share of the resident CTAs
-    // (about 5 per SM) instead of all of them, so that their grids run side by side
-    if (!getenv("PDEODE_PERSIST_MAX_CTAS")) {
-        char cap[32];
-        snprintf(cap, sizeof cap, "%d", std::max(64, 148 * 5 / per_gpu));
-        setenv("PDEODE_PERSIST_MAX_CTAS", cap, 1);
-    }
+    // members share a GPU: each member's cooperative launches (the whole-step kernel, the
+    // persistent solve) are capped to 64 CTAs, so that at least two members' grids are
+    // resident side by side -- one fills the other's barrier waits -- and the rest take turns.
+    // Measured with 32 members of 512^2, 16 in flight (profiles/README.md): caps of 37 to 74
+    // CTAs all take 2.2-2.4 s, 24 CTAs 4.5 s, 92 CTAs (one member resident at a time) 6.5 s.
+    if (per_gpu > 1 && !getenv("PDEODE_PERSIST_MAX_CTAS") && !getenv("PDEODE_GPU_SHARE"))
+        setenv("PDEODE_PERSIST_MAX_CTAS", "64", 1);
+    // more member threads than cores is normal here: waiting threads give their core away
+    if (!getenv("PDEODE_STEP_YIELD")) setenv("PDEODE_STEP_YIELD", "1", 1);
 
     const int nmember = argc - 1;
     std::vector<int> rc((size_t)nmember, -1);
