@@ -133,6 +133,17 @@ int pdeode_get_frame_rowmeans(pdeode_ctx *ctx, int filter, double *meanM, double
 int pdeode_step(pdeode_ctx *ctx, int *countIters, long long *nitSum,
                 long long *nitMax);
 
+/* n time steps back to back: the stretch of the loop P:663-742 between two
+ * points where the host looks at the state (diagnostics P:665, frames P:683).
+ * What solveOrder2 accumulates over those steps comes back already summed /
+ * maximised: countSum for `avgIters = avgIters + countIters` (P:740), countMax
+ * for maxIters (P:739), nitSum for avgNit (P:723), nitMax for maxNit (P:722).
+ * On small grids (the whole-step engine) this is one launch and one host wait
+ * for all n steps; elsewhere it is n calls of pdeode_step.  stepsDone < n only
+ * with PDEODE_ERR_PICARD_CAP (the failing step is not counted) or an error. */
+int pdeode_step_many(pdeode_ctx *ctx, int n, int *stepsDone, long long *countSum,
+                     int *countMax, long long *nitSum, long long *nitMax);
+
 /* calcMass(M), calcMass(C) (P:667-668, P:772-791): grid means, global over
  * all ranks. */
 int pdeode_mass(pdeode_ctx *ctx, double *meanM, double *meanC);

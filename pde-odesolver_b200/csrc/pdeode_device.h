@@ -130,6 +130,10 @@ struct PersistArgs {
 // solveOrder2 keeps per time step (P:702,722-723,730) plus the buffer roles.
 constexpr int STEP_TRACE = 64;
 struct StepOut {
+    // over all time steps of the launch, as solveOrder2 accumulates them (P:722-723, P:739-740)
+    long long count_sum, nit_sum_all, nit_max_all;
+    int steps_done, count_max;
+    // the last time step of the launch
     long long nit_sum, nit_max;          // P:723, P:722
     long long nit[STEP_TRACE];           // CG iterations of each solve of the step
     double diffs[2 * STEP_TRACE];        // (diffC, diffM) after each Picard iterate (P:725-726)
@@ -151,6 +155,7 @@ struct StepArgs {
     StencilArgs st;        // grid, numbers, scalars, d, ac, r, q
     double *Mb[3], *Cb[3]; // the rotating field buffers
     int iM, iC;            // current iterate at entry; becomes Mprev / Cprev (P:703-704)
+    int nsteps;            // time steps in this launch
     int warm;              // 0: first solve ever, x0 = the zeroed buffer iMnew0 (D8)
     int iMnew0;
     double *pbuf[2];

@@ -825,13 +825,14 @@ int pdeode_get_frame_rowmeans(pdeode_ctx *c, int filter, double *meanM, double *
 namespace {
 
 // P:700-742 as one cooperative launch (k_step_persist) and one host wait.
-int step_whole(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nitMax) {
+int step_whole(pdeode_ctx *c, int nsteps) {
     c->seq++;
     StepArgs a{};
     a.st = stencil_args(c);
     a.st.trace = nullptr;
     for (int k = 0; k < 3; ++k) { a.Mb[k] = c->Mb[k]; a.Cb[k] = c->Cb[k]; }
     a.iM = c->iM; a.iC = c->iC;
+    a.nsteps = nsteps;
     a.warm = c->warm ? 1 : 0;
     a.iMnew0 = c->iMnew;
     a.pbuf[0] = c->pbuf[0]; a.pbuf[1] = c->pbuf[1]; a.ip = c->ip;
@@ -877,7 +878,7 @@ int step_whole(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nit
     c->step_gen = o.gen;
     c->iM = o.iM; c->iC = o.iC; c->iMnew = o.iMnew;
     c->ip = o.ip; c->p = c->pbuf[c->ip];
-    c->warm = c->warm || o.count > 0;
+    c->warm = c->warm || o.count > 0 || o.steps_done > 0;
     c->mass_valid = false;
     c->trace_count = std::min(o.count, std::min(MAX_PICARD_TRACE, STEP_TRACE));
     for (int k = 0; k < c->trace_count; ++k) {
@@ -885,11 +886,13 @@ int step_whole(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nit
         c->diff_trace[2 * k] = o.diffs[2 * k];
         c->diff_trace[2 * k + 1] = o.diffs[2 * k + 1];
     }
-    if (countIters) *countIters = o.count;
-    if (nitSum) *nitSum = o.nit_sum;
-    if (nitMax) *nitMax = o.nit_max;
     if (o.picard_cap) return PDEODE_ERR_PICARD_CAP;
     return PDEODE_OK | (o.cg_cap ? PDEODE_WARN_CG_CAP : 0);
+}
+
+inline bool whole_step_path(const pdeode_ctx *c) {
+    // small grids, one rank, no per-iteration CG trace asked for
+    return c->cfg.whole_step && !multi(c) && c->trace_cap == 0;
 }
 
 }  // namespace
@@ -898,9 +901,15 @@ int step_whole(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nit
 int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nitMax) {
     if (!c) return PDEODE_ERR_ARG;
     CK(cudaSetDevice(c->device));
-    // small grids, one rank, no per-iteration CG trace asked for: the whole step in one launch
-    if (c->cfg.whole_step && !multi(c) && c->trace_cap == 0)
-        return step_whole(c, countIters, nitSum, nitMax);
+    if (whole_step_path(c)) {                        // the whole step in one launch
+        const int rc1 = step_whole(c, 1);
+        if ((rc1 & PDEODE_ERR_MASK) && (rc1 & PDEODE_ERR_MASK) != PDEODE_ERR_PICARD_CAP) return rc1;
+        const StepOut &o = *c->step_out_h;
+        if (countIters) *countIters = o.count;
+        if (nitSum) *nitSum = o.nit_sum;
+        if (nitMax) *nitMax = o.nit_max;
+        return rc1;
+    }
     int rc;
     int warn = 0;
     // Cprev = C ; Mprev = M (P:703-704): the current buffers become the frozen ones
@@ -986,6 +995,49 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
     if (nitSum) *nitSum = sum;
     if (nitMax) *nitMax = mx;
     return PDEODE_OK | warn;
+}
+
+// n time steps with what solveOrder2 accumulates over them (P:722-723, P:739-740)
+int pdeode_step_many(pdeode_ctx *c, int n, int *stepsDone, long long *countSum, int *countMax,
+                     long long *nitSum, long long *nitMax) {
+    if (!c || n < 0) return PDEODE_ERR_ARG;
+    CK(cudaSetDevice(c->device));
+    int done = 0, cmax = 0, warn = 0, rc = PDEODE_OK;
+    long long csum = 0, nsum = 0, nmax = 0;
+    if (whole_step_path(c)) {
+        // one launch and one host wait per batch; the report holds STEP_TRACE-independent sums
+        while (done < n) {
+            const int batch = std::min(n - done, 4096);
+            rc = step_whole(c, batch);
+            const int err = rc & PDEODE_ERR_MASK;
+            if (err && err != PDEODE_ERR_PICARD_CAP) return rc;
+            const StepOut &o = *c->step_out_h;
+            done += o.steps_done;
+            csum += o.count_sum; nsum += o.nit_sum_all;
+            cmax = std::max(cmax, o.count_max);
+            nmax = std::max(nmax, o.nit_max_all);
+            warn |= rc & PDEODE_WARN_CG_CAP;
+            if (err) break;
+            rc = PDEODE_OK;
+        }
+    } else {
+        for (; done < n; ++done) {
+            int cnt = 0; long long s1 = 0, m1 = 0;
+            rc = pdeode_step(c, &cnt, &s1, &m1);
+            if (rc & PDEODE_ERR_MASK) break;
+            warn |= rc & PDEODE_WARN_CG_CAP;
+            rc = PDEODE_OK;
+            csum += cnt; nsum += s1;
+            cmax = std::max(cmax, cnt);
+            nmax = std::max(nmax, m1);
+        }
+    }
+    if (stepsDone) *stepsDone = done;
+    if (countSum) *countSum = csum;
+    if (countMax) *countMax = cmax;
+    if (nitSum) *nitSum = nsum;
+    if (nitMax) *nitMax = nmax;
+    return (rc & PDEODE_ERR_MASK) ? rc : (PDEODE_OK | warn);
 }
 
 int pdeode_mass(pdeode_ctx *c, double *meanM, double *meanC) {

@@ -1548,9 +1548,21 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
     };
     stamp();
 
-    const int iMprev = A.iM, iCprev = A.iC;          // Mprev = M ; Cprev = C (P:703-704)
     int iM = A.iM, iC = A.iC, iMnew = A.iMnew0, ip = A.ip;
-    bool ok = true;
+    bool ok = true, warm = A.warm != 0;
+    double diffC = 1.0, diffM = 1.0;
+    int count = 0, cg_cap = 0, picard_cap = 0;
+    long long nsum = 0, nmax = 0;
+    double rho = 0.0, rho_old = 0.0, xx = 0.0, alfa = 0.0, err2 = 0.0, normx = 0.0, pq = 0.0, pp = 0.0;
+    long long it = 0;
+    int stop = 0;
+    // what the caller accumulates over time steps (P:722-723, P:739-740)
+    int steps_done = 0, count_max = 0;
+    long long count_sum = 0, nit_sum = 0, nit_max = 0;
+
+    // A.nsteps time steps back to back: nothing between two steps needs the host
+    for (int sidx = 0; sidx < A.nsteps; ++sidx) {
+    const int iMprev = iM, iCprev = iC;              // Mprev = M ; Cprev = C (P:703-704)
 
     // d = D(Mprev) on my rows and the rows above and below (the neighbours store
     // the same bits there); d left and right of a strip comes from other CTAs
@@ -1575,27 +1587,24 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
     }
     stamp();
 
-    double diffC = 1.0, diffM = 1.0;                 // P:700-701
-    int count = 0, cg_cap = 0, picard_cap = 0;       // P:702
-    long long nsum = 0, nmax = 0;
-    double rho = 0.0, rho_old = 0.0, xx = 0.0, alfa = 0.0, err2 = 0.0, normx = 0.0, pq = 0.0, pp = 0.0;
-    long long it = 0;
-    int stop = 0;
-    if (!(diffC + diffM > A.eSoln)) ok = false;      // P:706 on entry (eSoln >= 2: no iterate at all)
+    diffC = 1.0; diffM = 1.0;                        // P:700-701
+    count = 0;                                       // P:702
+    nsum = 0; nmax = 0;
+    const bool run = ok && (diffC + diffM > A.eSoln);   // P:706 on entry (eSoln >= 2: no iterate at all)
 
     // target of a solve: neither Mprev nor the current iterate; the very first
     // solve after set_state starts from (and into) the zeroed buffer (D8)
     int inew = 0;
     while (inew == iMprev || inew == iM) inew++;
-    if (!A.warm) inew = A.iMnew0;
+    if (!warm) inew = A.iMnew0;
     TilePtrs T;
     T.d = a.d; T.ac = a.ac; T.r = a.r; T.q = a.q; T.p = nullptr;
     T.Mprev = A.Mb[iMprev];
 
     // ---- first Picard iterate: centre diagonal, r = b - A x0 (P:712, CG:46-50)
-    if (ok) {
+    if (run) {
         T.Cc = A.Cb[iC];
-        T.x0 = A.warm ? A.Mb[iM] : A.Mb[inew];
+        T.x0 = warm ? A.Mb[iM] : A.Mb[inew];
         T.x = A.Mb[inew];
         VecLoad<MODE_INIT> V;
         V.a = T.x0; V.b = nullptr; V.first = true; V.beta = 0.0;
@@ -1605,7 +1614,7 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
         rho = acc[0]; xx = acc[1];                   // CG:53
         stamp();
     }
-    while (ok) {                                     // P:706, left by the breaks below
+    while (run && ok) {                              // P:706, left by the breaks below
         double *const x = A.Mb[inew];
         // ---- solveLSDIAG (CG:54-94)
         it = 0; stop = 0; rho_old = 0.0;             // CG:44,53
@@ -1713,8 +1722,18 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
         if (!(diffC + diffM > A.eSoln)) break;       // P:706
         rho = acc[2]; xx = acc[3];                   // CG:53 of the next solve
     }
+    if (!ok || picard_cap) break;
+    warm = warm || count > 0;
+    ++steps_done;
+    count_sum += count;                              // P:740
+    if (count > count_max) count_max = count;        // P:739
+    nit_sum += nsum;
+    if (nmax > nit_max) nit_max = nmax;
+    }   // time steps
     if (blockIdx.x == 0 && tid == 0) {
         StepOut *o = A.out;
+        o->steps_done = steps_done; o->count_sum = count_sum; o->count_max = count_max;
+        o->nit_sum_all = nit_sum; o->nit_max_all = nit_max;
         o->nit_sum = nsum; o->nit_max = nmax; o->count = count;
         o->cg_cap = cg_cap; o->picard_cap = picard_cap;
         o->error = (*(volatile unsigned int *)err != 0u) ? 1 : 0;

@@ -60,6 +60,14 @@ module pdeode_b200
             integer(c_int), intent(out) :: countIters
             integer(c_long_long), intent(out) :: nitSum, nitMax
         end function
+        integer(c_int) function pdeode_step_many(ctx, n, stepsDone, countSum, countMax, nitSum, nitMax) &
+                bind(C, name="pdeode_step_many")
+            import :: c_ptr, c_int, c_long_long
+            type(c_ptr), value :: ctx
+            integer(c_int), value :: n
+            integer(c_int), intent(out) :: stepsDone, countMax
+            integer(c_long_long), intent(out) :: countSum, nitSum, nitMax
+        end function
 
         integer(c_int) function pdeode_mass(ctx, meanM, meanC) bind(C, name="pdeode_mass")
             import :: c_ptr, c_int, c_double

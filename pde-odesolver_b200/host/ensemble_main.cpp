@@ -33,7 +33,7 @@ int main(int argc, char **argv) {
     }
     pdeode_host::Stepper st{};
     st.create = pdeode_create; st.set_state = pdeode_set_state; st.get_state = pdeode_get_state;
-    st.step = pdeode_step; st.mass = pdeode_mass; st.peak = pdeode_peak;
+    st.step = pdeode_step; st.step_many = pdeode_step_many; st.mass = pdeode_mass; st.peak = pdeode_peak;
     st.destroy = pdeode_destroy; st.strerror_ = pdeode_strerror;
     st.frame_size = pdeode_frame_size; st.get_frame = pdeode_get_frame;
     st.get_frame_rowmeans = pdeode_get_frame_rowmeans;

@@ -14,7 +14,7 @@ int main() {
     st.create = pdeode_create;
     st.set_state = pdeode_set_state;
     st.get_state = pdeode_get_state;
-    st.step = pdeode_step;
+    st.step = pdeode_step; st.step_many = pdeode_step_many;
     st.mass = pdeode_mass;
     st.peak = pdeode_peak;
     st.destroy = pdeode_destroy;

@@ -606,10 +606,24 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
             fflush(con);
         }
         t_frame += since(tf);
-        int countIters = 0;
-        long long nitSum = 0, nitMax = 0;
+        // the stretch up to the next point where the loop looks at the state (P:665, P:683)
+        // or ends (P:663) goes to the device in one call
+        int batch = 1;
+        if (st.step_many) {
+            const long long cad = (long long)(filter / 100 + 1);
+            while (batch < 4096 && (counter + batch) % cad != 0 && (counter + batch) % filter != 0 &&
+                   (double)(counter + batch) * tDel <= tEnd)
+                ++batch;
+        }
+        int countIters = 0, stepsDone = 1;
+        long long countSum = 0, nitSum = 0, nitMax = 0;
         const auto ts = now();
-        rc = st.step(ctx, &countIters, &nitSum, &nitMax);                        // P:700-738
+        if (batch > 1) {
+            rc = st.step_many(ctx, batch, &stepsDone, &countSum, &countIters, &nitSum, &nitMax);
+        } else {
+            rc = st.step(ctx, &countIters, &nitSum, &nitMax);                    // P:700-738
+            countSum = countIters;
+        }
         t_step += since(ts);
         have_host_copy = false;
         if ((rc & PDEODE_ERR_MASK) == PDEODE_ERR_PICARD_CAP) {                   // P:732-736
@@ -624,8 +638,8 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
         if ((double)nitMax > maxNit) maxNit = (double)nitMax;                    // P:722
         avgNit = avgNit + (double)nitSum;                                        // P:723
         if (countIters > maxIters) maxIters = countIters;                        // P:739
-        avgIters = avgIters + countIters;                                        // P:740
-        counter = counter + 1;                                                   // P:742
+        avgIters = avgIters + (double)countSum;                                  // P:740
+        counter = counter + stepsDone;                                           // P:742
     }
     avgNit = avgNit / avgIters;                                                  // P:744
     avgIters = avgIters / counter;                                               // P:745

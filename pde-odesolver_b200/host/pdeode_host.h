@@ -81,6 +81,9 @@ struct Stepper {
     // optional: build the initial fields on the device instead of uploading them
     int (*set_initial_condition)(pdeode_ctx *, int, double, double, int, const double *,
                                  const double *);
+    // optional: several time steps with one host wait (pdeode_step_many); without it the
+    // loop calls step once per time step
+    int (*step_many)(pdeode_ctx *, int, int *, long long *, int *, long long *, long long *);
 };
 
 // What pdeode_set_initial_condition needs: the case and its inoculation points.

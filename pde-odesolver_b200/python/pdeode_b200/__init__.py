@@ -80,6 +80,7 @@ def _lib():
         "pdeode_get_state": [vp, vp, vp],
         "pdeode_set_initial_condition": [vp, C.c_int, C.c_double, C.c_double, C.c_int, vp, vp],
         "pdeode_step": [vp, ip, llp, llp],
+        "pdeode_step_many": [vp, C.c_int, ip, llp, ip, llp, llp],
         "pdeode_frame_size": [vp, C.c_int, ip, ip],
         "pdeode_get_frame": [vp, C.c_int, vp, vp],
         "pdeode_get_frame_rowmeans": [vp, C.c_int, vp, vp],
@@ -223,6 +224,17 @@ class Solver:
         if (rc & ERR_MASK) not in (OK, ERR_PICARD_CAP):
             self._ck(rc, "step")
         return dict(rc=rc, countIters=cnt.value, nitSum=s.value, nitMax=mx.value)
+
+    def step_many(self, n):
+        """n time steps with one host wait where the engine allows (pdeode_step_many)."""
+        done, cmax = C.c_int(), C.c_int()
+        csum, nsum, nmax = C.c_longlong(), C.c_longlong(), C.c_longlong()
+        rc = self.lib.pdeode_step_many(self.h, n, C.byref(done), C.byref(csum), C.byref(cmax),
+                                       C.byref(nsum), C.byref(nmax))
+        if (rc & ERR_MASK) not in (OK, ERR_PICARD_CAP):
+            self._ck(rc, "step_many")
+        return dict(rc=rc, stepsDone=done.value, countSum=csum.value, countMax=cmax.value,
+                    nitSum=nsum.value, nitMax=nmax.value)
 
     def step_trace(self, cap=64):
         info = self.step()

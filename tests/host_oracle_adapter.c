@@ -79,10 +79,12 @@ typedef struct {
      * whole-field writer path -- the GPU run takes the other, and the two are compared */
     void *frame_size, *get_frame, *get_frame_rowmeans;
     void *set_initial_condition;    /* absent: the host builds the fields itself */
+    void *step_many;                /* absent: one step call per time step */
 } stepper_table;
 
 static const stepper_table TABLE = {a_create, a_set_state, a_get_state, a_step,
                                     a_mass,   a_peak,      a_destroy,   a_strerror,
-                                    0,        0,           0,           0};
+                                    0,        0,           0,           0,
+                                    0};
 
 const void *oracle_stepper_table(void) { return &TABLE; }

@@ -408,6 +408,36 @@ def test_set_state_resets_warm_start(pb):
     s.close()
 
 
+@pytest.mark.parametrize("engine", ["whole-step", "persistent", "kernels"])
+@pytest.mark.parametrize("row,col", [(65, 65), (257, 4), (129, 200)])
+def test_step_many_equals_single_steps(pb, engine_env, engine, row, col):
+    """pdeode_step_many(n) -- one launch and one host wait on the whole-step engine --
+    must leave exactly the state and the sums that n calls of pdeode_step leave."""
+    engine_env(engine)
+    M0, C0 = ol.ic1(row, col, 0.9, 0.3)
+    a = pb.Solver(row, col, pb.default_params(row))
+    b = pb.Solver(row, col, pb.default_params(row))
+    a.set_state(M0, C0); b.set_state(M0, C0)
+    n = 7
+    singles = [a.step() for _ in range(n)]
+    many = b.step_many(n)
+    assert many["rc"] == 0 and many["stepsDone"] == n
+    assert many["countSum"] == sum(r["countIters"] for r in singles)
+    assert many["countMax"] == max(r["countIters"] for r in singles)
+    assert many["nitSum"] == sum(r["nitSum"] for r in singles)
+    assert many["nitMax"] == max(r["nitMax"] for r in singles)
+    Ma, Ca = a.get_state(); Mb, Cb = b.get_state()
+    assert np.array_equal(Ma, Mb) and np.array_equal(Ca, Cb)
+    # and the two keep agreeing when the calls are mixed
+    ra = [a.step() for _ in range(2)]; rb = b.step_many(2)
+    assert rb["nitSum"] == sum(r["nitSum"] for r in ra)
+    rb1 = b.step(); ra1 = a.step_many(1)
+    assert rb1["nitSum"] == ra1["nitSum"] and rb1["countIters"] == ra1["countSum"]
+    Ma, Ca = a.get_state(); Mb, Cb = b.get_state()
+    assert np.array_equal(Ma, Mb) and np.array_equal(Ca, Cb)
+    a.close(); b.close()
+
+
 # ------------------------------------------------------------ device-side frame decimation
 
 @pytest.mark.parametrize("row,col,filt", [(33, 33, 1), (1025, 1025, 4), (513, 300, 2), (1025, 4, 4)])

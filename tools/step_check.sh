@@ -1,5 +1,9 @@
 #!/bin/bash
 mkdir -p gpurun_out
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "whole or bit_exact or long_run or cap or warm" > gpurun_out/pytest_step.log 2>&1
-echo "pytest exit $?"; tail -n 4 gpurun_out/pytest_step.log
-timeout 300 python tools/step_bench.py --grids 257,512,1024 --steps 300 --groups 1,2,3 --engines whole-step 2>/dev/null | cut -c1-150
+timeout 900 python -m pytest tests -m gpu -q > gpurun_out/pytest_gpu.log 2>&1
+echo "pytest exit $?"; tail -n 6 gpurun_out/pytest_gpu.log
+R=$GRAFT_REPO_ROOT
+mkdir -p /tmp/w1 && cd /tmp/w1
+for f in shipped257.txt shipped257_wave.txt; do
+echo "$R/tests/data/$f" | PDEODE_HOST_TIMING=1 PDEODE_SEED=1 $R/pde-odesolver_b200/bin/pdeode_solver 2>&1 | grep "Time to compute\|host timing\|Avg Iters"
+done
