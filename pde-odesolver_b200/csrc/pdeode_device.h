@@ -121,8 +121,9 @@ struct PersistArgs {
     double *x;             // CG iterate (Mnew)
     double *pbuf[2];       // direction, ping-pong; pbuf[ip] is read by the first iteration
     int ip;
-    double *red;           // [2][2][G] partial sums of the grid-wide reductions
-    unsigned int *bar;     // {arrival count, generation} of the grid barrier
+    double *slots;         // [2][G][4] partial sums of the grid-wide sums (persist_allsum)
+    unsigned long long *counter;   // arrivals at grid-wide sums since the context was created
+    unsigned long long gen0;       // number of grid-wide sums of earlier launches
     int nstrips, nchunks;  // G = nstrips * nchunks CTAs, one tile each
 };
 

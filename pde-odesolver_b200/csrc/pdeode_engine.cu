@@ -54,14 +54,16 @@ struct pdeode_ctx {
     bool warm = false;            // false until the first solve: x0 = 0 (D8)
 
     DevScal *S = nullptr;
-    double *red = nullptr;            // persistent solve: grid-wide reduction buffers
-    unsigned int *bar = nullptr;      // persistent solve: grid barrier
+    unsigned int *bar = nullptr;      // bar[2]: error word of the whole-step launch
     StepOut *step_out_h = nullptr;    // whole-step launch: its report, mapped host memory
     StepOut *step_out = nullptr;      // the same, device-side address
     bool step_poll = true;            // wait for the report by watching its sequence word
     bool step_yield = false;          // PDEODE_STEP_YIELD=1: give the core away between looks (ensembles)
     bool step_stamps = false;         // PDEODE_STEP_STAMPS=1: print CTA 0's phase times of every step to stderr
     unsigned long long step_seq = 0;
+    double *persist_slots = nullptr;  // persistent solve: partial sums and arrival counter of its grid-wide sums
+    unsigned long long *persist_counter = nullptr;
+    unsigned long long persist_gen = 0;
     double *step_slots = nullptr;     // whole-step launch: partial sums and arrival counter of its grid-wide sums
     unsigned long long *step_counter = nullptr;
     unsigned long long step_gen = 0;
@@ -277,7 +279,7 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         pa.st.defer_x = c->cfg.persist_defer ? 1 : 0;
         pa.x = x;
         pa.pbuf[0] = c->pbuf[0]; pa.pbuf[1] = c->pbuf[1]; pa.ip = c->ip;
-        pa.red = c->red; pa.bar = c->bar;
+        pa.slots = c->persist_slots; pa.counter = c->persist_counter; pa.gen0 = c->persist_gen;
         pa.nstrips = c->cfg.p_nstrips; pa.nchunks = c->cfg.p_nchunks;
         CK(launch_cg_persist(pa, c->cfg.p_BS, c->stream));
         c->launches++;
@@ -545,9 +547,12 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     {
         const size_t G = (size_t)std::max(1, std::max(c->cfg.p_nstrips * c->cfg.p_nchunks,
                                                       c->cfg.s_nstrips * c->cfg.s_nchunks));
-        CK(cudaMalloc(&c->red, sizeof(double) * 6 * G));
         CK(cudaMalloc(&c->bar, 4 * sizeof(unsigned int)));
         CK(cudaMemset(c->bar, 0, 4 * sizeof(unsigned int)));
+        CK(cudaMalloc(&c->persist_slots, sizeof(double) * 8 * G));
+        CK(cudaMemset(c->persist_slots, 0, sizeof(double) * 8 * G));
+        CK(cudaMalloc(&c->persist_counter, sizeof(unsigned long long)));
+        CK(cudaMemset(c->persist_counter, 0, sizeof(unsigned long long)));
     }
     if (nranks > 1) c->cfg.whole_step = 0;              // one rank only
     if (c->cfg.whole_step) {
@@ -647,11 +652,12 @@ int pdeode_destroy(pdeode_ctx *c) {
     for (int k = 0; k < pdeode_ctx::NARR; ++k) if (c->base[k]) cudaFree(c->base[k]);
     if (c->partials) cudaFree(c->partials);
     if (c->frame_buf) cudaFree(c->frame_buf);
-    if (c->red) cudaFree(c->red);
     if (c->bar) cudaFree(c->bar);
     if (c->step_out_h) cudaFreeHost(c->step_out_h);
     if (c->step_slots) cudaFree(c->step_slots);
     if (c->step_counter) cudaFree(c->step_counter);
+    if (c->persist_slots) cudaFree(c->persist_slots);
+    if (c->persist_counter) cudaFree(c->persist_counter);
     if (c->S) cudaFree(c->S);
     if (c->trace) cudaFree(c->trace);
     if (c->gather) cudaFree(c->gather);
@@ -965,6 +971,7 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
                 return PDEODE_ERR_CUDA;
             }
             c->phase += 2ULL * (unsigned long long)fin.nit;   // two exchanges per iteration
+            c->persist_gen += 2ULL * (unsigned long long)fin.nit;   // = two grid-wide sums
             c->ip = c->pending_ip0 ^ (int)(fin.nit & 1);
             c->p = c->pbuf[c->ip];
             nit = fin.nit;

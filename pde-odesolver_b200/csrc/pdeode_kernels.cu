@@ -225,6 +225,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
+__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -239,10 +244,10 @@ __device__ __forceinline__ double ld_relaxed_sys(const double *p) {
 // rank order (the same order on every rank, so every rank gets the same bits).
 // A peer that never posts (crashed) makes the wait give up after ~1 s of GPU
 // clocks and raise DevScal::error instead of hanging the device.
-__device__ __forceinline__ void peer_wait_sums(const PeerComm &pc, unsigned long long phase,
+__device__ __forceinline__ bool peer_wait_sums(const PeerComm &pc, unsigned long long phase,
                                                DevScal *S, double &s0, double &s1,
                                                double *s2 = nullptr) {
-    __shared__ double sh[3];
+    __shared__ double sh[4];
     if (threadIdx.x == 0) {
         const int slot = (int)(phase % PEER_SLOTS);
         const unsigned long long *f = pc.flags + slot * PEER_MAX_RANKS;
@@ -261,12 +266,14 @@ __device__ __forceinline__ void peer_wait_sums(const PeerComm &pc, unsigned long
             c += ld_relaxed_sys(v + PEER_VALS * r + 2);
         }
         if (!ok) S->error = 1;
-        sh[0] = a; sh[1] = b; sh[2] = c;
+        sh[0] = a; sh[1] = b; sh[2] = c; sh[3] = ok ? 1.0 : 0.0;
     }
     __syncthreads();
     s0 = sh[0]; s1 = sh[1];
     if (s2) *s2 = sh[2];
+    const bool all_ok = sh[3] != 0.0;
     __syncthreads();
+    return all_ok;
 }
 
 // One thread: store this rank's pair into every rank's comm block, then raise
@@ -1098,56 +1105,6 @@ __global__ void __launch_bounds__(256) k_xtail(double *__restrict__ x, const dou
 
 // ---------------------------------------------------------------- persistent CG solve
 
-// Grid-wide barrier for a cooperative launch (all CTAs resident): one arrival
-// counter and a generation word in global memory.  The generation is read
-// before arriving, so a CTA that races ahead into the next barrier cannot be
-// mistaken for a late arrival of this one.
-__device__ __forceinline__ void grid_barrier(unsigned int *bar, unsigned int G, bool sys) {
-    if (sys) __threadfence_system();    // peer mode: ghost rows stored into other GPUs
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        volatile unsigned int *gen = bar + 1;
-        const unsigned int g0 = *gen;
-        __threadfence();
-        if (atomicAdd(bar, 1u) == G - 1) {
-            bar[0] = 0u;
-            __threadfence();
-            atomicAdd(bar + 1, 1u);
-        } else {
-            while (*gen == g0) { }
-        }
-        __threadfence();
-    }
-    __syncthreads();
-}
-
-// Grid-wide sum of a pair: every CTA stores its partial, all meet at the
-// barrier, then every CTA adds all partials in the same fixed order -- every
-// CTA (and, in peer mode, every rank) ends up with the same bits, so each can
-// take the stop decision on its own.  red: [2][G] doubles.
-// Grid-wide sum of a pair: every CTA stores its partial, all meet at the
-// barrier, then every CTA adds all partials in the same fixed order -- every
-// CTA (and, in peer mode, every rank) ends up with the same bits, so each can
-// take the stop decision on its own.  red: [2][G] doubles.  (Measured against a
-// variant where only warp 0 re-adds the partials: this one is faster, 1.93e11
-// against 1.63e11 on 4 GPUs at 4096^2.)
-__device__ __forceinline__ void grid_allsum2(double &a, double &b, double *red, unsigned int *bar,
-                                             int G, double *sm, double *s_tot, bool sys) {
-    block_sum2(a, b, sm);
-    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; }
-    grid_barrier(bar, (unsigned int)G, sys);
-    double x = 0.0, y = 0.0;
-    for (int i = threadIdx.x; i < G; i += blockDim.x) {
-        x += __ldcg(red + i);
-        y += __ldcg(red + G + i);
-    }
-    block_sum2(x, y, sm);
-    if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; }
-    __syncthreads();
-    a = s_tot[0]; b = s_tot[1];
-    __syncthreads();
-}
-
 // Sum of a triple over the block with one barrier pair; result in thread 0.  sm: 96 doubles.
 __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, double *sm) {
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
@@ -1163,30 +1120,78 @@ __device__ __forceinline__ void block_sum3(double &a, double &b, double &c, doub
     }
 }
 
-// Grid-wide sum of a triple: every CTA stores its partial, all meet at the
-// barrier, then warp 0 of every CTA adds all partials in the same fixed order
-// (lane l takes partials l, l+32, ...; then a shuffle tree) -- every CTA, and
-// in peer mode every rank, ends up with the same bits, so each can take the
-// stop decision on its own.  red: [3][G] doubles, sm: 96 doubles.
-__device__ __forceinline__ void grid_allsum3(double &a, double &b, double &c, double *red,
-                                             unsigned int *bar, int G, double *sm, double *s_tot,
-                                             bool sys) {
+// Grid-wide (and, in peer mode, all-rank) sum of a triple for the persistent
+// solve.  Every CTA stores its partial sums in its own slot, fences, and adds
+// one to an arrival counter that only grows (sum number `gen`, counted over the
+// life of the context, is complete at gen * G) -- see step_allsum for the
+// single-GPU timing of this against a counter + generation word.
+//   one rank:  thread 0 of every CTA watches the counter (acquire), then all
+//              CTAs add the G slots in slot order: same bits everywhere.
+//   peer mode: nobody watches the counter.  The CTA whose arrival completes it
+//              adds the slots and posts the rank's sums into every rank's comm
+//              block over NVLink; every CTA of every rank waits for all ranks'
+//              flags there and adds the posted sums in rank order.  The local
+//              release word, the re-add in every CTA and the separate
+//              post-after-barrier step of a two-level scheme are gone.
+// Slots alternate between two sets (gen & 1): a CTA reaches gen+2 only after
+// gen+1 is complete, i.e. after whoever read the slots of gen has arrived
+// there.  slots: [2][G][4] doubles.
+__device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, double *slots,
+                                               unsigned long long *counter,
+                                               const unsigned long long gen, const int G,
+                                               const bool peer, const bool wrote_peer,
+                                               const PeerComm &pc, const unsigned long long ph,
+                                               DevScal *S, double *sm, double *s_tot) {
+    __shared__ int s_last, s_bad;
+    const int tid = threadIdx.x;
+    if (tid == 0) s_bad = 0;
+    double *const my_slots = slots + (size_t)(gen & 1ULL) * G * 4;
+    const unsigned long long target = gen * (unsigned long long)G;
     block_sum3(a, b, c, sm);
-    if (threadIdx.x == 0) { red[blockIdx.x] = a; red[G + blockIdx.x] = b; red[2 * G + blockIdx.x] = c; }
-    grid_barrier(bar, (unsigned int)G, sys);
-    if (threadIdx.x < 32) {
-        double x = 0.0, y = 0.0, w = 0.0;
-        for (int i = threadIdx.x; i < G; i += 32) {
-            x += __ldcg(red + i);
-            y += __ldcg(red + G + i);
-            w += __ldcg(red + 2 * G + i);
+    if (tid == 0) {
+        double *o = my_slots + 4 * blockIdx.x;
+        st2(o, make_double2(a, b));
+        st2(o + 2, make_double2(c, 0.0));
+        // release: my CTA's field stores (ordered before this by the barrier inside
+        // block_sum3) and the slot; system-wide if rows went into a neighbour GPU
+        if (wrote_peer) __threadfence_system();
+        else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+        if (peer) {
+            const unsigned long long old = atomicAdd(counter, 1ULL);
+            s_last = (old + 1ULL == target);
+            if (s_last) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire the others' slots
+        } else {
+            atomicAdd(counter, 1ULL);
+            const long long t0 = clock64();
+            unsigned spins = 0;
+            while (ld_acquire_gpu(counter) < target) {
+                if ((++spins & 255u) == 0u && clock64() - t0 > 4000000000LL) { S->error = 1; s_bad = 1; break; }
+            }
+            s_last = 1;                  // one rank: every CTA adds the slots
         }
-        x = warp_sum(x); y = warp_sum(y); w = warp_sum(w);
-        if (threadIdx.x == 0) { s_tot[0] = x; s_tot[1] = y; s_tot[2] = w; }
     }
     __syncthreads();
-    a = s_tot[0]; b = s_tot[1]; c = s_tot[2];
+    if (s_last) {
+        double x = 0.0, y = 0.0, z = 0.0;
+        for (int i = tid; i < G; i += blockDim.x) {
+            const double *o = my_slots + 4 * i;
+            const double2 u = __ldcg(reinterpret_cast<const double2 *>(o));
+            const double2 w = __ldcg(reinterpret_cast<const double2 *>(o + 2));
+            x += u.x; y += u.y; z += w.x;
+        }
+        __syncthreads();                 // block_sum3's scratch is free again
+        block_sum3(x, y, z, sm);
+        if (tid == 0) {
+            if (peer) peer_post(pc, ph, x, y, z);
+            else { s_tot[0] = x; s_tot[1] = y; s_tot[2] = z; }
+        }
+    }
+    if (peer) return peer_wait_sums(pc, ph, S, a, b, &c);     // barriers inside
     __syncthreads();
+    a = s_tot[0]; b = s_tot[1]; c = s_tot[2];
+    const bool ok = (s_bad == 0);
+    __syncthreads();
+    return ok;
 }
 
 // The whole CG solve (CG:54-94) in one cooperative launch: every CTA owns one
@@ -1241,7 +1246,8 @@ k_cg_persist(const PersistArgs A) {
     double *const dn = peer && a.pc.r_dn ? a.pc.r_dn - g.P : nullptr;
 
     long long K = 0, it = 0;
-    int ip = A.ip, stop = 0, sel = 0;
+    int ip = A.ip, stop = 0;
+    unsigned long long gen = A.gen0;
     double alfa = 0.0, err2 = 0.0, normx = 0.0, pq = 0.0, pp = 0.0;
     for (;;) {
         ++it;                                                        // CG:55
@@ -1264,13 +1270,10 @@ k_cg_persist(const PersistArgs A) {
                                     defer ? A.x : nullptr, alfa, &acc2);
         }
         K += (i_end - i_begin) + 2;
-        if (defer) grid_allsum3(acc0, acc1, acc2, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, false);
-        else grid_allsum2(acc0, acc1, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, false);
-        sel ^= 1;
-        if (peer) {
-            ++ph;
-            if (blockIdx.x == 0 && tid == 0) peer_post(a.pc, ph, acc0, acc1, acc2);
-            peer_wait_sums(a.pc, ph, S, acc0, acc1, &acc2);
+        ++ph; ++gen;
+        if (!persist_allsum(acc0, acc1, acc2, A.slots, A.counter, gen, G, peer, false, a.pc, ph, S, sm, s_tot)) {
+            stop = -1;                       // an exchange timed out (DevScal::error is set): leave
+            break;
         }
         pq = acc0; pp = acc1;
         if (defer && !firstit) xx = acc2;                            // CG:57
@@ -1325,12 +1328,11 @@ k_cg_persist(const PersistArgs A) {
         }
         // only CTAs that stored into a neighbour GPU need the system-wide fence
         const bool wrote_peer = (up && i_begin == 0) || (dn && i_end == g.rows);
-        grid_allsum2(rr, xn, A.red + (size_t)sel * 3 * G, A.bar, G, sm, s_tot, wrote_peer);
-        sel ^= 1;
-        if (peer) {
-            ++ph;
-            if (blockIdx.x == 0 && tid == 0) peer_post(a.pc, ph, rr, xn);
-            peer_wait_sums(a.pc, ph, S, rr, xn);
+        double zz = 0.0;
+        ++ph; ++gen;
+        if (!persist_allsum(rr, xn, zz, A.slots, A.counter, gen, G, peer, wrote_peer, a.pc, ph, S, sm, s_tot)) {
+            stop = -1;
+            break;
         }
         rho_old = rho; rho = rr;                                     // CG:56,59
         if (!defer) xx = xn;                                         // CG:57
@@ -1397,11 +1399,6 @@ __global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
 
 // ---------------------------------------------------------------- whole time step, one launch
 
-__device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 // Grid-wide sum of NV values that is also the grid barrier, for a cooperative
 // launch (all CTAs resident).  Every CTA publishes its partial sums in its own
 // slot, fences, and adds one to an arrival counter that only ever grows: sum
