@@ -72,7 +72,7 @@ enum {
 
 constexpr int PEER_MAX_RANKS = 8;
 constexpr int PEER_SLOTS = 4;    // phases in flight never span more than two slots
-constexpr int PEER_VALS = 4;     // doubles per (slot, rank): up to three sums + pad
+constexpr int PEER_VALS = 6;     // 8-byte words per (slot, rank): three sums as LL words (peer_post)
 
 // Peer-memory exchange of one context (multi rank).  Every rank owns a comm
 // block {slots[PEER_SLOTS][PEER_MAX_RANKS][PEER_VALS], flags[PEER_SLOTS][PEER_MAX_RANKS]}

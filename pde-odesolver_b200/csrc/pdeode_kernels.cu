@@ -116,7 +116,8 @@ __device__ __forceinline__ bool grid_sum2(double &a, double &b, double *partials
     }
     __syncthreads();
     if (!s_last) return false;
-    __threadfence();
+    if (sysfence) __threadfence_system();   // a peer_post follows: acquire here, release to all GPUs
+    else __threadfence();
     double x = 0.0, y = 0.0;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) {
         x += __ldcg(partials + i);
@@ -147,7 +148,8 @@ __device__ __forceinline__ bool grid_sum3(double &a, double &b, double &c, doubl
     }
     __syncthreads();
     if (!s_last3) return false;
-    __threadfence();
+    if (sysfence) __threadfence_system();
+    else __threadfence();
     double x = 0.0, y = 0.0, z = 0.0, z1 = 0.0;
     for (int i = threadIdx.x; i < nb; i += blockDim.x) {
         x += __ldcg(partials + i);
@@ -220,11 +222,6 @@ __global__ void k_scal_after_solvec(DevScal *S, GridDesc g) {
 
 // ---------------------------------------------------------------- peer-memory exchange
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
     unsigned long long v;
     asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
@@ -233,40 +230,80 @@ __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long
 __device__ __forceinline__ void st_relaxed_sys(unsigned long long *p, unsigned long long v) {
     asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
-__device__ __forceinline__ double ld_relaxed_sys(const double *p) {
-    double v;
-    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys_u64(const unsigned long long *p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
 
-// All threads of the CTA call this.  Thread 0 waits until every rank has
-// posted `phase` into this rank's comm block, then adds the posted pairs in
-// rank order (the same order on every rank, so every rank gets the same bits).
-// A peer that never posts (crashed) makes the wait give up after ~1 s of GPU
-// clocks and raise DevScal::error instead of hanging the device.
+// Posted sums travel as "LL" words: every 8-byte word carries 32 bits of
+// payload and the low 32 bits of the phase number, so a word is its own flag
+// (an aligned 8-byte store is indivisible) and the poster needs no fence
+// between data and flag -- one NVLink trip instead of a round trip plus a trip.
+// Three doubles = six words per (slot, rank).  A slot is reused every
+// PEER_SLOTS phases; stale words carry another tag and never match.
+__device__ __forceinline__ unsigned long long ll_word(unsigned int half, unsigned long long phase) {
+    return ((unsigned long long)half << 32) | (unsigned long long)(unsigned int)phase;
+}
+
+// All threads of the CTA call this.  Lane r of warp 0 watches the six words
+// rank r posts into this rank's comm block -- all ranks at once, six loads in
+// flight per lane -- until they carry this phase's tag, reads one of them
+// again as an acquire (the neighbours' ghost rows of r were complete before they posted),
+// and the eight lanes add the sums in a fixed tree: the same on every rank and
+// in every kernel, so every rank gets the same bits.  A peer that never posts
+// (crashed) makes the wait give up after ~1 s of GPU clocks and raise
+// DevScal::error instead of hanging the device.  Returns false in that case.
 __device__ __forceinline__ bool peer_wait_sums(const PeerComm &pc, unsigned long long phase,
                                                DevScal *S, double &s0, double &s1,
                                                double *s2 = nullptr) {
     __shared__ double sh[4];
-    if (threadIdx.x == 0) {
+    if (threadIdx.x < 32) {
+        const int lane = threadIdx.x;
         const int slot = (int)(phase % PEER_SLOTS);
-        const unsigned long long *f = pc.flags + slot * PEER_MAX_RANKS;
-        const double *v = pc.slots + (size_t)slot * PEER_MAX_RANKS * PEER_VALS;
-        const long long t0 = clock64();
+        const unsigned int tag = (unsigned int)phase;
+        double a = 0.0, b = 0.0, c = 0.0;
         bool ok = true;
-        for (int r = 0; r < pc.nranks && ok; ++r) {
-            while (ld_acquire_sys(f + r) < phase) {
+        if (lane < pc.nranks) {
+            const unsigned long long *w = reinterpret_cast<const unsigned long long *>(pc.slots) +
+                                          ((size_t)slot * PEER_MAX_RANKS + lane) * PEER_VALS;
+            unsigned long long w0, w1, w2, w3, w4, w5;
+            const long long t0 = clock64();
+            for (;;) {
+                w0 = ld_relaxed_sys_u64(w); w1 = ld_relaxed_sys_u64(w + 1);
+                w2 = ld_relaxed_sys_u64(w + 2); w3 = ld_relaxed_sys_u64(w + 3);
+                w4 = ld_relaxed_sys_u64(w + 4); w5 = ld_relaxed_sys_u64(w + 5);
+                if ((unsigned int)w0 == tag && (unsigned int)w1 == tag && (unsigned int)w2 == tag &&
+                    (unsigned int)w3 == tag && (unsigned int)w4 == tag && (unsigned int)w5 == tag)
+                    break;
                 if (clock64() - t0 > 2000000000LL) { ok = false; break; }
             }
+            // acquire without a MEMBAR.SYS (which costs microseconds in every CTA): one more
+            // look at a word that is already there, as an acquire load
+            (void)ld_acquire_sys(w);
+            a = __hiloint2double((int)(w1 >> 32), (int)(w0 >> 32));
+            b = __hiloint2double((int)(w3 >> 32), (int)(w2 >> 32));
+            c = __hiloint2double((int)(w5 >> 32), (int)(w4 >> 32));
+            if (!ok) { a = 0.0; b = 0.0; c = 0.0; }
         }
-        double a = 0.0, b = 0.0, c = 0.0;
-        for (int r = 0; r < pc.nranks; ++r) {
-            a += ld_relaxed_sys(v + PEER_VALS * r);
-            b += ld_relaxed_sys(v + PEER_VALS * r + 1);
-            c += ld_relaxed_sys(v + PEER_VALS * r + 2);
+        __syncwarp();
+        static_assert(PEER_MAX_RANKS == 8, "the tree below spans eight lanes");
+#pragma unroll
+        for (int o = 4; o > 0; o >>= 1) {
+            a += __shfl_xor_sync(FULL, a, o);
+            b += __shfl_xor_sync(FULL, b, o);
+            c += __shfl_xor_sync(FULL, c, o);
         }
-        if (!ok) S->error = 1;
-        sh[0] = a; sh[1] = b; sh[2] = c; sh[3] = ok ? 1.0 : 0.0;
+        ok = __all_sync(FULL, ok);
+        if (lane == 0) {
+            if (!ok) S->error = 1;
+            sh[0] = a; sh[1] = b; sh[2] = c; sh[3] = ok ? 1.0 : 0.0;
+        }
     }
     __syncthreads();
     s0 = sh[0]; s1 = sh[1];
@@ -276,19 +313,27 @@ __device__ __forceinline__ bool peer_wait_sums(const PeerComm &pc, unsigned long
     return all_ok;
 }
 
-// One thread: store this rank's pair into every rank's comm block, then raise
-// the flag there.  Ghost rows written earlier by other CTAs of this grid are
-// ordered before the flag by their own system fences (grid_sum2).
+// One thread: store this rank's sums, as LL words, into every rank's comm
+// block (its own included).  No fence here: whoever calls this has already
+// taken a system-scope fence after observing that all CTAs of this rank are
+// done (ticket / arrival counter), and the CTAs that stored ghost rows into a
+// neighbour GPU fenced system-wide before they signalled -- those rows are
+// complete at their destination before these words are even sent.
 __device__ __forceinline__ void peer_post(const PeerComm &pc, unsigned long long phase, double a,
                                           double b, double c = 0.0) {
     const int slot = (int)(phase % PEER_SLOTS);
+    const unsigned long long w0 = ll_word((unsigned int)__double2loint(a), phase);
+    const unsigned long long w1 = ll_word((unsigned int)__double2hiint(a), phase);
+    const unsigned long long w2 = ll_word((unsigned int)__double2loint(b), phase);
+    const unsigned long long w3 = ll_word((unsigned int)__double2hiint(b), phase);
+    const unsigned long long w4 = ll_word((unsigned int)__double2loint(c), phase);
+    const unsigned long long w5 = ll_word((unsigned int)__double2hiint(c), phase);
     for (int r = 0; r < pc.nranks; ++r) {
-        double *v = pc.peer_slots[r] + ((size_t)slot * PEER_MAX_RANKS + pc.rank) * PEER_VALS;
-        v[0] = a; v[1] = b; v[2] = c;
+        unsigned long long *w = reinterpret_cast<unsigned long long *>(pc.peer_slots[r]) +
+                                ((size_t)slot * PEER_MAX_RANKS + pc.rank) * PEER_VALS;
+        st_relaxed_sys(w, w0); st_relaxed_sys(w + 1, w1); st_relaxed_sys(w + 2, w2);
+        st_relaxed_sys(w + 3, w3); st_relaxed_sys(w + 4, w4); st_relaxed_sys(w + 5, w5);
     }
-    __threadfence_system();     // one fence, then plain flag stores: a release per flag would fence each
-    for (int r = 0; r < pc.nranks; ++r)
-        st_relaxed_sys(pc.peer_flags[r] + slot * PEER_MAX_RANKS + pc.rank, phase);
 }
 
 // ---------------------------------------------------------------- D(M)
@@ -1159,7 +1204,8 @@ __device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, 
         if (peer) {
             const unsigned long long old = atomicAdd(counter, 1ULL);
             s_last = (old + 1ULL == target);
-            if (s_last) asm volatile("fence.acq_rel.gpu;" ::: "memory");   // acquire the others' slots
+            // acquire the others' slots; system scope: a post to the other GPUs follows
+            if (s_last) asm volatile("fence.acq_rel.sys;" ::: "memory");
         } else {
             atomicAdd(counter, 1ULL);
             const long long t0 = clock64();
