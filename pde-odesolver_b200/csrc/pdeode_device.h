@@ -67,7 +67,8 @@ enum {
     SUMS_RAW = 0,    // rank-local sums into DevScal::part; NCCL all-reduce + a scalar kernel follow
     SUMS_FUSED = 1,  // single rank: the last CTA turns the sums into alfa / beta / stop itself
     SUMS_PEER = 2    // multi rank: the last CTA stores the sums into every rank's comm block over
-                     // NVLink; the next kernel's CTAs wait for all ranks' flags and add the slots
+                     // NVLink; the next kernel's CTAs wait until all ranks' words carry the phase
+                     // tag and add them
 };
 
 constexpr int PEER_MAX_RANKS = 8;
@@ -75,9 +76,11 @@ constexpr int PEER_SLOTS = 4;    // phases in flight never span more than two sl
 constexpr int PEER_VALS = 6;     // 8-byte words per (slot, rank): three sums as LL words (peer_post)
 
 // Peer-memory exchange of one context (multi rank).  Every rank owns a comm
-// block {slots[PEER_SLOTS][PEER_MAX_RANKS][PEER_VALS], flags[PEER_SLOTS][PEER_MAX_RANKS]}
-// that the other ranks write into through CUDA-IPC mappings; r_up / r_dn are the
-// neighbours' residual arrays, whose ghost rows this rank fills directly.
+// block slots[PEER_SLOTS][PEER_MAX_RANKS][PEER_VALS] of 8-byte LL words (32 bits
+// of payload + the low 32 bits of the phase number: peer_post / peer_wait_sums in
+// pdeode_kernels.cu) that the other ranks write into through CUDA-IPC mappings;
+// the flags area behind it is allocated but no longer used.  r_up / r_dn are
+// the neighbours' residual arrays, whose ghost rows this rank fills directly.
 struct PeerComm {
     int rank, nranks;
     const double *slots;                       // local comm block, written by peers
