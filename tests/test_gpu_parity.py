@@ -216,6 +216,7 @@ def test_first_cg_iteration_scalars(pb):
     (50, 300, dict(fSelect=6, dSelect=2, alpha=2), ("blobs", 0.3, 0.2, 5, 1), 3),
     (64, 64, dict(dSelect=1, fSelect=5, tDel=1e-2), ("blobs", 0.3, 0.3, 4, 2), 3),
     (257, 257, {}, ("blobs", 0.02, 0.0390625, 60, 7), 4),     # shipped parameter.txt values
+    (24, 1100, {}, ("ic1", 0.9, 0.3), 3),                     # wider than one 1024-column strip
 ])
 @pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent", "register-staged",
                                     "whole-step"])
