@@ -1185,6 +1185,7 @@ __device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, 
                                                unsigned long long *counter,
                                                const unsigned long long gen, const int G,
                                                const bool peer, const bool wrote_peer,
+                                               const bool rows_went_out,
                                                const PeerComm &pc, const unsigned long long ph,
                                                DevScal *S, double *sm, double *s_tot) {
     __shared__ int s_last, s_bad;
@@ -1204,8 +1205,13 @@ __device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, 
         if (peer) {
             const unsigned long long old = atomicAdd(counter, 1ULL);
             s_last = (old + 1ULL == target);
-            // acquire the others' slots; system scope: a post to the other GPUs follows
-            if (s_last) asm volatile("fence.acq_rel.sys;" ::: "memory");
+            // acquire the others' slots.  System scope where this phase stored ghost rows
+            // into the neighbour GPUs (the post that follows releases them to all ranks);
+            // after the SpMV phase nothing but the sums themselves crosses NVLink
+            if (s_last) {
+                if (rows_went_out) asm volatile("fence.acq_rel.sys;" ::: "memory");
+                else asm volatile("fence.acq_rel.gpu;" ::: "memory");
+            }
         } else {
             atomicAdd(counter, 1ULL);
             const long long t0 = clock64();
@@ -1317,7 +1323,7 @@ k_cg_persist(const PersistArgs A) {
         }
         K += (i_end - i_begin) + 2;
         ++ph; ++gen;
-        if (!persist_allsum(acc0, acc1, acc2, A.slots, A.counter, gen, G, peer, false, a.pc, ph, S, sm, s_tot)) {
+        if (!persist_allsum(acc0, acc1, acc2, A.slots, A.counter, gen, G, peer, false, false, a.pc, ph, S, sm, s_tot)) {
             stop = -1;                       // an exchange timed out (DevScal::error is set): leave
             break;
         }
@@ -1376,7 +1382,7 @@ k_cg_persist(const PersistArgs A) {
         const bool wrote_peer = (up && i_begin == 0) || (dn && i_end == g.rows);
         double zz = 0.0;
         ++ph; ++gen;
-        if (!persist_allsum(rr, xn, zz, A.slots, A.counter, gen, G, peer, wrote_peer, a.pc, ph, S, sm, s_tot)) {
+        if (!persist_allsum(rr, xn, zz, A.slots, A.counter, gen, G, peer, wrote_peer, peer, a.pc, ph, S, sm, s_tot)) {
             stop = -1;
             break;
         }
