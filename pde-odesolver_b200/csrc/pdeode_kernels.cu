@@ -104,7 +104,7 @@ __device__ __forceinline__ bool grid_sum2(double &a, double &b, double *partials
                                           bool sysfence = false) {
     __shared__ int s_last;
     // peer mode: this CTA may have stored ghost rows into a neighbour GPU; they
-    // must be visible system-wide before the last CTA raises the flag
+    // must be visible system-wide before the last CTA posts the sums
     if (sysfence) __threadfence_system();
     block_sum2(a, b, sm);
     if (threadIdx.x == 0) {
@@ -1252,9 +1252,9 @@ __device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, 
 //   B: x += alfa p ; r -= alfa q ; r.r ; x.x     (its own cells only)
 // with one grid-wide sum after each.  All CTAs hold the same scalars and take
 // the same stop decision (CG:87-90), so no kernel boundary, host round trip
-// or scalar broadcast is needed per iteration; in peer mode CTA 0 also trades
-// the sums with the other GPUs and boundary rows of r go straight into the
-// neighbours' ghost rows.  Used where launch latency would dominate (small
+// or scalar broadcast is needed per iteration; in peer mode the CTA that
+// completes a grid-wide sum also posts it to the other GPUs (persist_allsum)
+// and boundary rows of r go straight into the neighbours' ghost rows.  Used where launch latency would dominate (small
 // grids, thin slabs of a multi-GPU run); results are bit-identical to the
 // kernel-per-phase path only up to the order of the partial sums.
 template <int BS, int DEPTH, bool DEFER>
