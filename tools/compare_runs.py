@@ -30,7 +30,10 @@ def main():
             worst = max(worst, e)
             out.append(f"relL2({name}) = {e:.3e}")
         print(f"frame {k:3d}: " + "  ".join(out))
-    tg, tc = np.loadtxt(f"{g}/total.dat"), np.loadtxt(f"{c}/total.dat")
+    def table(path):                     # a run still in progress ends in a partial line
+        rows = [l.split() for l in open(path)]
+        return np.array([[float(v) for v in r] for r in rows if len(r) == 3])
+    tg, tc = table(f"{g}/total.dat"), table(f"{c}/total.dat")
     m = min(len(tg), len(tc))
     print(f"total.dat: {m} common samples; max |d mean M| = {np.abs(tg[:m, 1] - tc[:m, 1]).max():.3e}, "
           f"max |d mean C| = {np.abs(tg[:m, 2] - tc[:m, 2]).max():.3e}; final mean M {tg[m - 1, 1]:.6f}")

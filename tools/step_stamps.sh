@@ -1,7 +1,8 @@
 #!/bin/bash
-# phase times of the whole-step launch (CTA 0) for a few steps
-mkdir -p gpurun_out
-for gr in 1 3; do
-echo "groups=$gr"
-PDEODE_STEP_GROUPS=$gr PDEODE_STEP_STAMPS=1 timeout 120 python tools/step_bench.py --grids 257 --steps 3 --engines whole-step 2>&1 | grep -A1 "step stamps" | tail -4
+# Phase times of the whole-step launch as CTA 0 sees them (ns | SM clocks per phase):
+# D, centre diagonal + residual, then per CG iteration SpMV phase and update phase, then
+# C update + next diagonal; each ends in one grid-wide sum.
+for g in 257 512 1024; do
+  echo "grid $g"
+  PDEODE_STEP_STAMPS=1 timeout 120 python tools/step_bench.py --grids $g --steps 3 --engines whole-step 2>&1 | grep "step stamps" | tail -2
 done
