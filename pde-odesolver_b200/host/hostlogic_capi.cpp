@@ -112,6 +112,10 @@ int pdeode_host_write_frame_decimated(const char *path, const pdeode_host_params
     return 0;
 }
 
+int pdeode_host_steps_until_next_look(long long counter, int filter, double tDel, double tEnd) {
+    return steps_until_next_look(counter, filter, tDel, tEnd);
+}
+
 // Whole program (P:20-175) with the caller's stepper; param_file name is fed
 // to the prompt as stdin would be.  console_path receives the console text.
 int pdeode_host_run(const char *param_file, const char *outdir, const char *console_path,

@@ -415,6 +415,19 @@ bool report_stats(const std::string &path, double avgIters, double maxIters, dou
 
 // ---------------------------------------------------------------- the time loop
 
+// How many time steps the loop P:663-742 takes from `counter` on before it looks
+// at the state again: diagnostics when mod(counter, filter/100+1) == 0 (P:665), a
+// frame when mod(counter, filter) == 0 (P:683), the end when counter*tDel > tEnd
+// (P:663).  Always >= 1: the step at `counter` itself is due.
+int steps_until_next_look(long long counter, int filter, double tDel, double tEnd) {
+    const long long cad = (long long)(filter / 100 + 1);
+    int batch = 1;
+    while (batch < 4096 && (counter + batch) % cad != 0 && (counter + batch) % filter != 0 &&
+           (double)(counter + batch) * tDel <= tEnd)
+        ++batch;
+    return batch;
+}
+
 static std::string join(const std::string &dir, const char *name) {
     return dir.empty() ? std::string(name) : dir + "/" + name;
 }
@@ -608,13 +621,7 @@ RunStats solve_order2(const RunParams &p, std::vector<double> &M, std::vector<do
         t_frame += since(tf);
         // the stretch up to the next point where the loop looks at the state (P:665, P:683)
         // or ends (P:663) goes to the device in one call
-        int batch = 1;
-        if (st.step_many) {
-            const long long cad = (long long)(filter / 100 + 1);
-            while (batch < 4096 && (counter + batch) % cad != 0 && (counter + batch) % filter != 0 &&
-                   (double)(counter + batch) * tDel <= tEnd)
-                ++batch;
-        }
+        const int batch = st.step_many ? steps_until_next_look(counter, filter, tDel, tEnd) : 1;
         int countIters = 0, stepsDone = 1;
         long long countSum = 0, nitSum = 0, nitMax = 0;
         const auto ts = now();

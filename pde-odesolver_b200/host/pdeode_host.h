@@ -58,6 +58,8 @@ void print_to_file(FILE *f, const RunParams &p, const double *M, const double *C
 void print_to_file_2d(FILE *f, const RunParams &p, const double *M, const double *C);
 // The same frames from data decimated on the device (pdeode_get_frame*).
 void print_frame(FILE *f, const RunParams &p, int nro, int nco, const double *Md, const double *Cd);
+// Steps the time loop takes from `counter` on before it looks at the state again (P:663,665,683).
+int steps_until_next_look(long long counter, int filter, double tDel, double tEnd);
 void print_frame_2d(FILE *f, const RunParams &p, int nro, const double *meanM, const double *meanC);
 // reportStats (P:1019-1040)
 bool report_stats(const std::string &path, double avgIters, double maxIters, double avgNit,

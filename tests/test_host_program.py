@@ -191,6 +191,31 @@ def test_decimated_frame_writer_equals_full_field_writer(host, tmp_path, size):
     assert open(a, "rb").read() == open(b, "rb").read()
 
 
+@pytest.mark.parametrize("tEnd,tDel,nOuts", [(30.0, 1e-3, 90), (0.05, 1e-3, 5), (1.0, 1e-2, 7), (2.0, 1e-3, 3)])
+def test_batched_steps_visit_the_same_counters(host, tEnd, tDel, nOuts):
+    """The GPU program advances in batches (pdeode_step_many); the counters at which it
+    looks at the state -- diagnostics P:665, frames P:683, loop end P:663 -- must be the
+    ones the reference's one-step-at-a-time loop visits."""
+    host.pdeode_host_steps_until_next_look.argtypes = [C.c_longlong, C.c_int, C.c_double, C.c_double]
+    filt = int(tEnd / (nOuts * tDel))                      # P:638
+    cad = filt // 100 + 1
+    # the reference loop
+    looks, counter = [], 0
+    while counter * tDel <= tEnd:
+        if counter % cad == 0 or counter % filt == 0:
+            looks.append(counter)
+        counter += 1
+    steps_ref = counter
+    # the batched loop
+    got, counter = [], 0
+    while counter * tDel <= tEnd:
+        assert counter % cad == 0 or counter % filt == 0 or not got or counter - got[-1] >= 4096
+        got.append(counter)
+        counter += host.pdeode_host_steps_until_next_look(counter, filt, tDel, tEnd)
+    assert counter == steps_ref
+    assert [c for c in got if c % cad == 0 or c % filt == 0] == looks
+
+
 def test_whole_program_with_oracle_stepper(host, adapter, tmp_path):
     """`echo FILE | a.out` end to end: console text, files, cadences (S6)."""
     out = tmp_path / "run"; out.mkdir()
