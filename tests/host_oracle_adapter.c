@@ -32,6 +32,24 @@ static int a_create(pdeode_ctx **out, int row, int col, const pdeode_params *p, 
 }
 static int a_set_state(pdeode_ctx *c, const double *M, const double *C)
 {
+    /* ORACLE_PERTURB=eps: start from M*(1 +- eps), a pseudo-random sign per cell -- the size of
+     * rounding differences between two builders of the same initial condition.  Used to see how
+     * far two runs of the reference's own algorithm drift apart from such a start. */
+    const char *e = getenv("ORACLE_PERTURB");
+    if (e && atof(e) != 0.0) {
+        const double eps = atof(e);
+        const long n = (long)c->row * c->col;
+        double *Mp = (double *)malloc(sizeof(double) * (size_t)n);
+        if (!Mp) return PDEODE_ERR_NOMEM;
+        unsigned int h = 12345u;
+        for (long i = 0; i < n; ++i) {
+            h = h * 1664525u + 1013904223u;
+            Mp[i] = M[i] * (1.0 + ((h >> 16) & 1u ? eps : -eps));
+        }
+        oracle_set_state(c->o, Mp, C);
+        free(Mp);
+        return PDEODE_OK;
+    }
     oracle_set_state(c->o, M, C);
     return PDEODE_OK;
 }

@@ -11,7 +11,8 @@ import __graft_entry__ as ge
 import oracle_lib as ol
 ge.build_host(); ol.build_oracle()
 build = os.path.join(ROOT, "tests", "_build"); os.makedirs(build, exist_ok=True)
-so = os.path.join(build, "libhost_oracle_adapter_omp.so" if omp else "libhost_oracle_adapter.so")
+tag = os.environ.get("ADAPTER_TAG", "")          # a private copy while another run has the library mapped
+so = os.path.join(build, "libhost_oracle_adapter" + ("_omp" if omp else "") + tag + ".so")
 subprocess.check_call(["/usr/bin/gcc", "-O2", "-fPIC", "-shared", "-o", so, os.path.join(ROOT, "tests", "host_oracle_adapter.c"),
                        "-L" + ol.ORACLE_DIR, "-loracle_omp" if omp else "-loracle", "-Wl,-rpath," + ol.ORACLE_DIR])
 ad = C.CDLL(so); ad.oracle_stepper_table.restype = C.c_void_p
