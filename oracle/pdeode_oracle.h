@@ -6,12 +6,18 @@
  * --impl reference legs may load this library.  The product path
  * (pde-odesolver_b200/) never links, imports or executes it.
  *
- * PARITY UNPINNED: the reference ships no tests, golden vectors or sample
- * outputs, and no Fortran compiler exists in this image, so this restatement
- * could not be checked against the reference binary.  It is pinned instead by
- * the known-answer tests in tests/test_oracle_kat.py (row-sum identity,
- * homogeneous-state closed form, boundary structure, warm start) and by the
- * committed fixtures in tests/golden/ that were generated from it.
+ * PARITY PIN: no Fortran compiler exists in this image, so the gfortran binary
+ * of runAll.sh:6 cannot be built.  Instead oracle/f90c/f90toc.py translates the
+ * reference's three .f90 files, where they lie, statement by statement to C
+ * (language rules only; it knows nothing about the algorithm), oracle/Makefile
+ * compiles that with gcc -O3 into oracle/_ref/ (program + library), and
+ * tests/test_reference_pin.py holds this restatement to it BIT FOR BIT:
+ * every subroutine on random inputs, solveLSDIAG's iteration counts, whole
+ * solveOrder2 runs, and the whole program's output files.  Vectors produced by
+ * that build are committed as tests/golden/ref_*.npz (tests/test_golden_ref.py)
+ * so that the pin travels to boxes without /root/reference.  What remains
+ * unpinned is gfortran's own code generation (e.g. a different libgcc powi or
+ * an FMA-contracting target), which no test here can see.
  *
  * "P:" = /root/reference/PDE-ODEsolver.f90, "CG:" = /root/reference/CGdiag.f90.
  * All reals are 8 bytes (reference build: gfortran -O3 -fdefault-real-8,
