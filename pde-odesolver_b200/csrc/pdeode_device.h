@@ -71,6 +71,18 @@ enum {
                      // tag and add them
 };
 
+// PDEODE_SUM_ORDER=serial (verification only): every reduction the reference does with a
+// serial loop -- dotProd (CG:99-114), sum(sol*sol) / sum(p*p) (CG:57,87), calcDiff (P:956-960),
+// calcMass (P:783-787) -- is re-done in the reference's order, one term after the other in
+// cell order by one thread, so that a run is bit-identical to the serial CPU build.
+enum { SER_DOT = 0, SER_ABSDIFF = 1, SER_SUM = 2 };
+constexpr int SER_MAXJ = 4;      // reductions per pass
+constexpr int SER_CH = 256;      // cells staged per chunk
+struct SerialJob {
+    const double *a, *b;         // SER_DOT: sum a*b ; SER_ABSDIFF: sum |a - b| ; SER_SUM: sum a
+    int kind, pad;
+};
+
 constexpr int PEER_MAX_RANKS = 8;
 constexpr int PEER_SLOTS = 4;    // phases in flight never span more than two slots
 constexpr int PEER_VALS = 6;     // 8-byte words per (slot, rank): three sums as LL words (peer_post)
@@ -89,6 +101,7 @@ struct PeerComm {
     unsigned long long *peer_flags[PEER_MAX_RANKS];
     double *r_up, *r_dn;                       // origin (row 0, col 0) of the neighbours' r, or null
     int rows_up;                               // local rows of rank-1 (its bottom ghost row index)
+    long long timeout_clocks;                  // a wait for a peer gives up after this many GPU clocks
 };
 
 enum { TICKET_STENCIL = 0, TICKET_UPDATE = 1, TICKET_SOLVEC = 2, TICKET_MASS = 3 };
@@ -128,6 +141,8 @@ struct PersistArgs {
     unsigned long long *counter;   // arrivals at grid-wide sums since the context was created
     unsigned long long gen0;       // number of grid-wide sums of earlier launches
     int nstrips, nchunks;  // G = nstrips * nchunks CTAs, one tile each
+    int serial;            // PDEODE_SUM_ORDER=serial: CTA 0 re-does every sum in cell order
+    double *ser_out;       // [2][SER_MAXJ] results of those sums
 };
 
 // What one whole-step launch (k_step_persist) reports back: the quantities
@@ -175,6 +190,8 @@ struct StepArgs {
     StepOut *out;          // mapped host memory
     int stamps;            // 1: CTA 0 records a time stamp after every phase
     unsigned long long seq;
+    int serial;            // PDEODE_SUM_ORDER=serial: CTA 0 re-does every sum in cell order
+    double *ser_out;       // [2][SER_MAXJ] results of those sums
 };
 
 struct UpdateArgs {
@@ -225,6 +242,9 @@ cudaError_t launch_xtail(double *x, const double *p, const DevScal *S, long long
                          cudaStream_t st);
 cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st);
 cudaError_t launch_mass(const MassArgs &a, cudaStream_t st);
+// nj sums in the reference's serial order over the cells of g; out[0 .. nj)
+cudaError_t launch_serial_reduce(const GridDesc &g, const SerialJob *jobs, int nj, double *out,
+                                 cudaStream_t st);
 cudaError_t launch_init_cond(const GridDesc &g, int ic, double depth, double height, double xDel,
                              int npts, const double *px, const double *py, double *M, double *C,
                              cudaStream_t st);

@@ -90,6 +90,11 @@ struct pdeode_ctx {
     bool pending_persist = false;               // a persistent solve is queued, not yet read back
     int pending_ip0 = 0;
 
+    // PDEODE_SUM_ORDER=serial (verification, one rank): every reduction re-done in the
+    // reference's cell order by one thread, so that a run equals the serial CPU build bit for bit
+    bool serial = false;
+    double *ser_out = nullptr;                  // [2][SER_MAXJ], persistent kernels
+
     LaunchCfg cfg{256, 64, 4, 1};
     int pred[MAX_PICARD_TRACE];
     long long seq = 0;
@@ -144,7 +149,16 @@ inline bool defer_x(const pdeode_ctx *c) {
     return c->cfg.defer_x && (c->nranks == 1 || c->peer) && c->cfg.variant == 1 && !c->cfg.persist;
 }
 inline int sums_mode(const pdeode_ctx *c) {
+    if (c->serial) return SUMS_RAW;      // the kernels' own sums are discarded; see serial_sums
     return !multi(c) ? SUMS_FUSED : (c->peer ? SUMS_PEER : SUMS_RAW);
+}
+
+// PDEODE_SUM_ORDER=serial: up to SER_MAXJ sums in the reference's cell order, into out[]
+// (normally DevScal::part, where the scalar kernels of the SUMS_RAW path pick them up).
+int serial_sums(pdeode_ctx *c, const SerialJob *jobs, int nj, double *out) {
+    CK(launch_serial_reduce(c->g, jobs, nj, out, c->stream));
+    c->launches++;
+    return PDEODE_OK;
 }
 
 // ghost-row exchange with the slabs above and below (one row each way)
@@ -214,8 +228,12 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     c->ip ^= 1;                      // the direction just written is the current one
     c->p = c->pbuf[c->ip];
     if (mode == SUMS_RAW) {
-        int rc = allreduce_part(c, 2);
-        if (rc) return rc;
+        int rc;
+        if (c->serial) {                     // dotProd(p,q) (CG:76), sum(p*p) (CG:87)
+            const SerialJob jb[2] = {{c->p, c->q, SER_DOT, 0}, {c->p, c->p, SER_DOT, 0}};
+            if ((rc = serial_sums(c, jb, 2, c->S->part))) return rc;
+        }
+        if (multi(c) && (rc = allreduce_part(c, 2))) return rc;
         CK(launch_scal_after_spmv(c->S, c->g, c->np.tol2, a.trace, c->stream));
         c->launches++;
     }
@@ -234,8 +252,12 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     else CK(launch_update(u, c->stream));
     c->launches++;
     if (mode == SUMS_RAW) {
-        int rc = allreduce_part(c, 2);
-        if (rc) return rc;
+        int rc;
+        if (c->serial) {                     // dotProd(r,r) (CG:59), sum(sol*sol) (CG:57)
+            const SerialJob jb[2] = {{c->r, c->r, SER_DOT, 0}, {x, x, SER_DOT, 0}};
+            if ((rc = serial_sums(c, jb, 2, c->S->part))) return rc;
+        }
+        if (multi(c) && (rc = allreduce_part(c, 2))) return rc;
         CK(launch_scal_after_update(c->S, c->stream));
         c->launches++;
         rc = halo_exchange(c, c->r);
@@ -259,8 +281,12 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     CK(launch_stencil_init(a, c->stream));
     c->launches++;
     if (sums_mode(c) == SUMS_RAW) {
-        int rc = allreduce_part(c, 2);
-        if (rc) return rc;
+        int rc;
+        if (c->serial) {                     // dotProd(r,r), sum(sol*sol) of the start vector
+            const SerialJob jb[2] = {{c->r, c->r, SER_DOT, 0}, {x, x, SER_DOT, 0}};
+            if ((rc = serial_sums(c, jb, 2, c->S->part))) return rc;
+        }
+        if (multi(c) && (rc = allreduce_part(c, 2))) return rc;
         CK(launch_scal_after_init(c->S, c->stream));
         c->launches++;
         rc = halo_exchange(c, c->r);
@@ -268,7 +294,7 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     }
 
     const int ip0 = c->ip;
-    if (c->cfg.persist && sums_mode(c) != SUMS_RAW) {
+    if (c->cfg.persist && (sums_mode(c) != SUMS_RAW || c->serial)) {
         // the whole CG loop in one cooperative launch (k_cg_persist)
         PersistArgs pa{};
         pa.st = stencil_args(c);
@@ -281,6 +307,7 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         pa.pbuf[0] = c->pbuf[0]; pa.pbuf[1] = c->pbuf[1]; pa.ip = c->ip;
         pa.slots = c->persist_slots; pa.counter = c->persist_counter; pa.gen0 = c->persist_gen;
         pa.nstrips = c->cfg.p_nstrips; pa.nchunks = c->cfg.p_nchunks;
+        pa.serial = c->serial ? 1 : 0; pa.ser_out = c->ser_out;
         CK(launch_cg_persist(pa, c->cfg.p_BS, c->stream));
         c->launches++;
         // no wait here: the C update queues right behind, and the caller reads the
@@ -339,7 +366,8 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     }
     const DevScal &fin = c->snap[slot].s;
     if (fin.error) {
-        c->err = "peer exchange timed out (a rank stopped posting)";
+        c->err = multi(c) ? "peer exchange timed out (a rank stopped posting)"
+                          : "grid barrier of the persistent solve timed out";
         return PDEODE_ERR_CUDA;
     }
     // launches after convergence were no-ops: the direction of the last real
@@ -384,7 +412,12 @@ int run_mass(pdeode_ctx *c) {
     m.n2 = (long long)c->g.rows * c->g.P / 2;
     CK(launch_mass(m, c->stream));
     c->launches++;
-    int rc = snapshot(c, 0);
+    int rc;
+    if (c->serial) {                                 // calcMass in cell order (P:783-787)
+        const SerialJob jb[2] = {{m.M, nullptr, SER_SUM, 0}, {m.C, nullptr, SER_SUM, 0}};
+        if ((rc = serial_sums(c, jb, 2, &c->S->sumM))) return rc;
+    }
+    rc = snapshot(c, 0);
     if (rc) return rc;
     rc = wait_snapshot(c, 0);
     if (rc) return rc;
@@ -457,6 +490,13 @@ int setup_peer(pdeode_ctx *c) {
     for (int r = 0; r < nr; ++r) ok = ok && all[(size_t)r].ok;
     PeerComm pc{};
     pc.rank = c->rank; pc.nranks = nr;
+    {
+        // a wait for a peer gives up after this long (GPU clocks at ~2 GHz); generous by default:
+        // a descheduled peer process or a profiler replay must not turn into a failure
+        double ms = 10000.0;
+        if (const char *e = getenv("PDEODE_PEER_TIMEOUT_MS")) { const double v = atof(e); if (v > 0) ms = v; }
+        pc.timeout_clocks = (long long)(ms * 2.0e6);
+    }
     pc.slots = (const double *)c->comm_block;
     pc.flags = (const unsigned long long *)((char *)c->comm_block + slots_bytes);
     const size_t origin = (size_t)GUARD + (size_t)c->g.P;        // (row 0, col 0) inside an array
@@ -540,6 +580,17 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     c->pbuf[0] = origin(9); c->pbuf[1] = origin(11); c->ip = 0; c->p = c->pbuf[0];
 
     c->cfg = launch_config(c->g);
+    if (const char *so = getenv("PDEODE_SUM_ORDER")) {
+        if (strcmp(so, "serial") == 0) {
+            if (nranks > 1) { c->err = "PDEODE_SUM_ORDER=serial is a one-rank verification mode"; return PDEODE_ERR_ARG; }
+            c->serial = true;
+            c->cfg.defer_x = 0; c->cfg.persist_defer = 0;     // x.x is taken where the reference takes it
+            CK(cudaMalloc(&c->ser_out, sizeof(double) * 2 * SER_MAXJ));
+            CK(cudaMemset(c->ser_out, 0, sizeof(double) * 2 * SER_MAXJ));
+        } else if (strcmp(so, "tree") != 0 && so[0] != '\0') {
+            c->err = "PDEODE_SUM_ORDER must be 'tree' or 'serial'"; return PDEODE_ERR_ARG;
+        }
+    }
     // the marching kernels never launch more CTAs than stencil_max_blocks(g, TR)
     c->max_blocks = std::max(stencil_max_blocks(c->g, std::min(std::min(c->cfg.TR, c->cfg.TR_x), c->cfg.i_TR)),
                              std::max(stream_blocks(), 512));
@@ -658,6 +709,7 @@ int pdeode_destroy(pdeode_ctx *c) {
     if (c->step_counter) cudaFree(c->step_counter);
     if (c->persist_slots) cudaFree(c->persist_slots);
     if (c->persist_counter) cudaFree(c->persist_counter);
+    if (c->ser_out) cudaFree(c->ser_out);
     if (c->S) cudaFree(c->S);
     if (c->trace) cudaFree(c->trace);
     if (c->gather) cudaFree(c->gather);
@@ -727,6 +779,8 @@ int pdeode_set_initial_condition(pdeode_ctx *c, int ic, double depth, double hei
     CK(cudaSetDevice(c->device));
     c->iM = c->iMprev = 0; c->iC = c->iCprev = 0; c->iMnew = 1;
     double *dp = nullptr;
+    // the point list is freed on every path out of here
+    struct Free { double *&p; ~Free() { if (p) { cudaFree(p); p = nullptr; } } } free_dp{dp};
     if (pts && npts > 0) {
         CK(cudaMalloc(&dp, sizeof(double) * 2 * (size_t)npts));
         CK(cudaMemcpyAsync(dp, px, sizeof(double) * (size_t)npts, cudaMemcpyHostToDevice, c->stream));
@@ -751,7 +805,6 @@ int pdeode_set_initial_condition(pdeode_ctx *c, int ic, double depth, double hei
     c->warm = false;
     c->mass_valid = false;
     CK(cudaStreamSynchronize(c->stream));
-    if (dp) CK(cudaFree(dp));
     return PDEODE_OK;
 }
 
@@ -849,6 +902,7 @@ int step_whole(pdeode_ctx *c, int nsteps) {
     a.eSoln = c->params.eSoln;
     a.picard_cap = PICARD_CAP;
     a.out = c->step_out;
+    a.serial = c->serial ? 1 : 0; a.ser_out = c->ser_out;
     c->iMprev = c->iM; c->iCprev = c->iC;            // P:703-704
     a.seq = ++c->step_seq;
     CK(launch_step_persist(a, c->cfg.s_BS, c->stream));
@@ -948,12 +1002,16 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         s.Mprev = c->Mb[c->iMprev]; s.Mnew = c->Mb[inew]; s.Cprev = c->Cb[c->iCprev];
         s.Ccur = c->Cb[c->iC]; s.Mcur = c->Mb[c->iM]; s.Cnew = c->Cb[icnew];
         s.n2 = (long long)c->g.rows * c->g.P / 2;
-        s.fuse_scalars = multi(c) ? 0 : 1;
+        s.fuse_scalars = (multi(c) || c->serial) ? 0 : 1;
         s.seq = c->seq;
         CK(launch_solvec(s, c->stream));             // P:717, P:725-726
         c->launches++;
-        if (multi(c)) {
-            if ((rc = allreduce_part(c, 2))) return rc;
+        if (c->serial) {                             // calcDiff x2 in cell order (P:956-960)
+            const SerialJob jb[2] = {{s.Ccur, s.Cnew, SER_ABSDIFF, 0}, {s.Mcur, s.Mnew, SER_ABSDIFF, 0}};
+            if ((rc = serial_sums(c, jb, 2, c->S->part))) return rc;
+        }
+        if (multi(c) || c->serial) {
+            if (multi(c) && (rc = allreduce_part(c, 2))) return rc;
             CK(launch_scal_after_solvec(c->S, c->g, c->stream));
             c->launches++;
         }
@@ -967,11 +1025,13 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
             const DevScal &fin = c->snap[0].s;
             c->pending_persist = false;
             if (fin.error) {
-                c->err = "peer exchange timed out (a rank stopped posting)";
+                c->err = multi(c) ? "peer exchange timed out (a rank stopped posting)"
+                          : "grid barrier of the persistent solve timed out";
                 return PDEODE_ERR_CUDA;
             }
             c->phase += 2ULL * (unsigned long long)fin.nit;   // two exchanges per iteration
-            c->persist_gen += 2ULL * (unsigned long long)fin.nit;   // = two grid-wide sums
+            // = two grid-wide sums per iteration (serial order: each is followed by a second barrier)
+            c->persist_gen += (c->serial ? 4ULL : 2ULL) * (unsigned long long)fin.nit;
             c->ip = c->pending_ip0 ^ (int)(fin.nit & 1);
             c->p = c->pbuf[c->ip];
             nit = fin.nit;
@@ -1017,7 +1077,7 @@ int pdeode_step_many(pdeode_ctx *c, int n, int *stepsDone, long long *countSum, 
             const int batch = std::min(n - done, 4096);
             rc = step_whole(c, batch);
             const int err = rc & PDEODE_ERR_MASK;
-            if (err && err != PDEODE_ERR_PICARD_CAP) return rc;
+            if (err && err != PDEODE_ERR_PICARD_CAP) break;      // the outputs below are still filled
             const StepOut &o = *c->step_out_h;
             done += o.steps_done;
             csum += o.count_sum; nsum += o.nit_sum_all;
@@ -1149,14 +1209,14 @@ int pdeode_engine_info(const pdeode_ctx *c, char *buf, int len) {
     if (!c || !buf || len < 1) return PDEODE_ERR_ARG;
     snprintf(buf, (size_t)len,
              "spmv=%s BS=%d TR=%d depth=%d init_BS=%d init_TR=%d persist=%d persist_ctas=%d "
-             "defer_x=%d kb_reverse=%d whole_step=%d step_BS=%d step_ctas=%d exchange=%s",
+             "defer_x=%d kb_reverse=%d whole_step=%d step_BS=%d step_ctas=%d exchange=%s sum_order=%s",
              c->cfg.variant == 1 ? "bulk-async" : "register-staged", c->cfg.BS, c->cfg.TR,
              c->cfg.DEPTH, c->cfg.i_BS, c->cfg.i_TR, c->cfg.persist,
              c->cfg.p_nstrips * c->cfg.p_nchunks,
              (c->cfg.persist && sums_mode(c) != SUMS_RAW ? c->cfg.persist_defer != 0 : defer_x(c)) ? 1 : 0,
              c->cfg.kb_reverse, c->cfg.whole_step, c->cfg.s_BS,
              c->cfg.s_nstrips * c->cfg.s_nchunks,
-             !multi(c) ? "none" : (c->peer ? "peer" : "nccl"));
+             !multi(c) ? "none" : (c->peer ? "peer" : "nccl"), c->serial ? "serial" : "tree");
     return PDEODE_OK;
 }
 

@@ -19,6 +19,7 @@
 // Picard iterate.
 #include "pdeode_device.h"
 
+#include <atomic>
 #include <cstdlib>
 
 namespace pdeode {
@@ -26,6 +27,7 @@ namespace pdeode {
 namespace {
 
 constexpr unsigned FULL = 0xffffffffu;
+constexpr int MAX_DEVICES = 64;
 
 int g_stream_ctas_per_sm = 16;   // grid of the streaming kernels, in CTAs per SM
 int g_num_sms = 148;
@@ -220,6 +222,76 @@ __global__ void k_scal_after_solvec(DevScal *S, GridDesc g) {
     scal_after_solvec(S, S->part[0], S->part[1], g.n_glob);
 }
 
+// ---------------------------------------------------------------- serial-order sums (verification)
+
+// PDEODE_SUM_ORDER=serial.  nj reductions over the cells of the grid in the
+// reference's order: acc = 0; acc = acc + term(cell) for cell = 1 .. n (row
+// major), exactly the loops of dotProd (CG:108-112), sum(sol*sol) (CG:57),
+// calcDiff (P:956-960) and calcMass (P:783-787).  The terms -- u*v, |a-b|, a --
+// are the same bits whoever computes them, so all threads of the CTA stage a
+// chunk of terms in shared memory (stage: [2][SER_MAXJ][SER_CH] doubles) while
+// thread 0 adds the previous chunk one term after the other.  All threads of the
+// CTA call this; out[0 .. nj) is written by thread 0.  Loads bypass L1: inside
+// the persistent kernels the arrays were written by other CTAs of the same launch.
+__device__ __forceinline__ void serial_reduce(const GridDesc &g, const SerialJob *jobs, const int nj,
+                                              double *stage, double *out) {
+    const long long n = (long long)g.rows * g.col;
+    const int nt = blockDim.x, tid = threadIdx.x;
+    auto fill = [&](long long c0, double *buf) {
+        for (int e = tid; e < SER_CH; e += nt) {
+            const long long k = c0 + e;
+            if (k >= n) break;
+            const long long i = k / g.col;
+            const long long off = i * g.P + (k - i * g.col);
+            for (int q = 0; q < nj; ++q) {
+                const double a = __ldcg(jobs[q].a + off);
+                double t = a;
+                if (jobs[q].kind == SER_DOT) t = a * __ldcg(jobs[q].b + off);
+                else if (jobs[q].kind == SER_ABSDIFF) t = fabs(a - __ldcg(jobs[q].b + off));
+                buf[q * SER_CH + e] = t;
+            }
+        }
+    };
+    double acc[SER_MAXJ];
+#pragma unroll
+    for (int q = 0; q < SER_MAXJ; ++q) acc[q] = 0.0;
+    __syncthreads();                     // the staging area may still be read by a previous call
+    fill(0, stage);
+    __syncthreads();
+    int cur = 0;
+    for (long long c0 = 0; c0 < n; c0 += SER_CH) {
+        const double *buf = stage + (size_t)cur * SER_MAXJ * SER_CH;
+        if (c0 + SER_CH < n) fill(c0 + SER_CH, stage + (size_t)(cur ^ 1) * SER_MAXJ * SER_CH);
+        if (tid == 0) {
+            const int len = (int)((n - c0 < SER_CH) ? (n - c0) : SER_CH);
+            for (int e = 0; e < len; ++e) {
+#pragma unroll
+                for (int q = 0; q < SER_MAXJ; ++q)
+                    if (q < nj) acc[q] = acc[q] + buf[q * SER_CH + e];
+            }
+        }
+        __syncthreads();
+        cur ^= 1;
+    }
+    if (tid == 0) {
+#pragma unroll
+        for (int q = 0; q < SER_MAXJ; ++q)
+            if (q < nj) out[q] = acc[q];
+    }
+}
+
+struct SerialArgs {
+    GridDesc g;
+    SerialJob job[SER_MAXJ];
+    int nj;
+    double *out;
+};
+
+__global__ void __launch_bounds__(256) k_serial_reduce(const SerialArgs a) {
+    __shared__ double stage[2 * SER_MAXJ * SER_CH];
+    serial_reduce(a.g, a.job, a.nj, stage, a.out);
+}
+
 // ---------------------------------------------------------------- peer-memory exchange
 
 __device__ __forceinline__ unsigned long long ld_acquire_gpu(const unsigned long long *p) {
@@ -257,8 +329,11 @@ __device__ __forceinline__ unsigned long long ll_word(unsigned int half, unsigne
 // again as an acquire (the neighbours' ghost rows of r were complete before they posted),
 // and the eight lanes add the sums in a fixed tree: the same on every rank and
 // in every kernel, so every rank gets the same bits.  A peer that never posts
-// (crashed) makes the wait give up after ~1 s of GPU clocks and raise
-// DevScal::error instead of hanging the device.  Returns false in that case.
+// (crashed) makes the wait give up after PeerComm::timeout_clocks GPU clocks
+// (PDEODE_PEER_TIMEOUT_MS, default 10 s) and raise DevScal::error instead of
+// hanging the device.  Returns false in that case; the caller must then leave
+// without storing anything (the sums are zeros) and mark the solve finished so
+// that the launches queued behind it return at once.
 __device__ __forceinline__ bool peer_wait_sums(const PeerComm &pc, unsigned long long phase,
                                                DevScal *S, double &s0, double &s1,
                                                double *s2 = nullptr) {
@@ -281,7 +356,7 @@ __device__ __forceinline__ bool peer_wait_sums(const PeerComm &pc, unsigned long
                 if ((unsigned int)w0 == tag && (unsigned int)w1 == tag && (unsigned int)w2 == tag &&
                     (unsigned int)w3 == tag && (unsigned int)w4 == tag && (unsigned int)w5 == tag)
                     break;
-                if (clock64() - t0 > 2000000000LL) { ok = false; break; }
+                if (clock64() - t0 > pc.timeout_clocks) { ok = false; break; }
             }
             // acquire without a MEMBAR.SYS (which costs microseconds in every CTA): one more
             // look at a word that is already there, as an acquire load
@@ -816,7 +891,10 @@ k_spmv_bulk(const StencilArgs a) {
     if (a.fuse_scalars == SUMS_PEER) {
         // dotProd(r,r) and sum(sol*sol) of the previous phase arrive from all ranks;
         // the neighbours' flags also cover the ghost rows of r they wrote here
-        peer_wait_sums(a.pc, a.wait_phase, S, rr_glob, xx_glob);
+        if (!peer_wait_sums(a.pc, a.wait_phase, S, rr_glob, xx_glob)) {
+            if (threadIdx.x == 0) { S->done = 1; S->finished = 1; }   // error: nothing is stored
+            return;
+        }
         beta = firstit ? 0.0 : rr_glob / S->rho;                   // S->rho still holds rho_old
     } else {
         beta = firstit ? 0.0 : S->rho / S->rho_old;                // CG:68
@@ -1031,7 +1109,10 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     const bool r_only = a.r_only != 0;          // 88-byte iteration: x belongs to the SpMV kernel
     double alfa, pq_glob = 0.0, pp_glob = 0.0, xx_post = 0.0;
     if (peer) {
-        peer_wait_sums(a.pc, a.wait_phase, S, pq_glob, pp_glob, &xx_post);   // dotProd(p,q), sum(p*p)
+        if (!peer_wait_sums(a.pc, a.wait_phase, S, pq_glob, pp_glob, &xx_post)) {   // dotProd(p,q), sum(p*p)
+            if (threadIdx.x == 0) { S->done = 1; S->finished = 1; }   // error: nothing is stored
+            return;
+        }
         alfa = S->rho / pq_glob;                                   // CG:77
     } else {
         alfa = S->alfa;
@@ -1246,6 +1327,24 @@ __device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, 
     return ok;
 }
 
+// PDEODE_SUM_ORDER=serial (one rank) inside the persistent solve: behind the grid-wide sum --
+// which is then only the barrier -- CTA 0 re-does the two sums in the reference's cell order,
+// and a second barrier hands the result to every CTA.
+__device__ __forceinline__ bool persist_serial(const SerialJob *jb, double &v0, double &v1,
+                                            const PersistArgs &A, const GridDesc &g, double *stage,
+                                            unsigned &nser, unsigned long long &gen,
+                                            const unsigned long long ph, double *sm, double *s_tot) {
+    double *slot = A.ser_out + (size_t)(nser++ & 1u) * SER_MAXJ;
+    if (blockIdx.x == 0) serial_reduce(g, jb, 2, stage, slot);
+    double z0 = 0.0, z1 = 0.0, z2 = 0.0;
+    ++gen;
+    if (!persist_allsum(z0, z1, z2, A.slots, A.counter, gen, (int)gridDim.x, false, false, false,
+                        A.st.pc, ph, A.st.S, sm, s_tot))
+        return false;
+    v0 = __ldcg(slot); v1 = __ldcg(slot + 1);
+    return true;
+}
+
 // The whole CG solve (CG:54-94) in one cooperative launch: every CTA owns one
 // tile (a 2*BS-column strip x a row range) for the entire solve and alternates
 //   A: p = r + beta p ; q = A p ; p.q ; p.p      (bulk-async staged, as k_spmv_bulk)
@@ -1257,13 +1356,16 @@ __device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, 
 // and boundary rows of r go straight into the neighbours' ghost rows.  Used where launch latency would dominate (small
 // grids, thin slabs of a multi-GPU run); results are bit-identical to the
 // kernel-per-phase path only up to the order of the partial sums.
-template <int BS, int DEPTH, bool DEFER>
+// SERIAL = PDEODE_SUM_ORDER=serial, a separate instantiation so that the production kernel
+// pays neither registers nor shared memory for it.
+template <int BS, int DEPTH, bool DEFER, bool SERIAL = false>
 __global__ void __launch_bounds__(BS + 32, (BS == 256 ? 2 : (BS == 128 ? 3 : 5)))
 k_cg_persist(const PersistArgs A) {
     constexpr int TC = Ring<BS, DEPTH>::TC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double sm[96];
     __shared__ double s_tot[3];
+    __shared__ double s_stage[SERIAL ? 2 * SER_MAXJ * SER_CH : 1];
     Ring<BS, DEPTH> R;
     R.carve(smem_raw);
 
@@ -1287,7 +1389,10 @@ k_cg_persist(const PersistArgs A) {
     unsigned long long ph = a.wait_phase;
     double rho, xx, rho_old = 0.0;
     if (peer) {
-        peer_wait_sums(a.pc, ph, S, rho, xx);          // posted by the INIT kernel
+        if (!peer_wait_sums(a.pc, ph, S, rho, xx)) {   // posted by the INIT kernel
+            if (blockIdx.x == 0 && tid == 0) { S->nit = 0; S->stop = -1; S->done = 1; S->finished = 1; }
+            return;
+        }
     } else {
         rho = S->rho; xx = S->xx;
     }
@@ -1301,6 +1406,7 @@ k_cg_persist(const PersistArgs A) {
     int ip = A.ip, stop = 0;
     unsigned long long gen = A.gen0;
     double alfa = 0.0, err2 = 0.0, normx = 0.0, pq = 0.0, pp = 0.0;
+    unsigned nser = 0;                   // PDEODE_SUM_ORDER=serial: see persist_serial
     for (;;) {
         ++it;                                                        // CG:55
         const bool firstit = (it == 1);
@@ -1326,6 +1432,10 @@ k_cg_persist(const PersistArgs A) {
         if (!persist_allsum(acc0, acc1, acc2, A.slots, A.counter, gen, G, peer, false, false, a.pc, ph, S, sm, s_tot)) {
             stop = -1;                       // an exchange timed out (DevScal::error is set): leave
             break;
+        }
+        if (SERIAL) {                        // dotProd(p,q) (CG:76), sum(p*p) (CG:87)
+            const SerialJob jb[2] = {{p_out, a.q, SER_DOT, 0}, {p_out, p_out, SER_DOT, 0}};
+            if (!persist_serial(jb, acc0, acc1, A, g, s_stage, nser, gen, ph, sm, s_tot)) { stop = -1; break; }
         }
         pq = acc0; pp = acc1;
         if (defer && !firstit) xx = acc2;                            // CG:57
@@ -1385,6 +1495,10 @@ k_cg_persist(const PersistArgs A) {
         if (!persist_allsum(rr, xn, zz, A.slots, A.counter, gen, G, peer, wrote_peer, peer, a.pc, ph, S, sm, s_tot)) {
             stop = -1;
             break;
+        }
+        if (SERIAL) {                        // dotProd(r,r) (CG:59), sum(sol*sol) (CG:57)
+            const SerialJob jb[2] = {{a.r, a.r, SER_DOT, 0}, {A.x, A.x, SER_DOT, 0}};
+            if (!persist_serial(jb, rr, xn, A, g, s_stage, nser, gen, ph, sm, s_tot)) { stop = -1; break; }
         }
         rho_old = rho; rho = rr;                                     // CG:56,59
         if (!defer) xx = xn;                                         // CG:57
@@ -1538,6 +1652,25 @@ __device__ __forceinline__ bool step_allsum(double (&v)[NV], double *slots,
     return bad == 0;
 }
 
+// PDEODE_SUM_ORDER=serial for the whole-step kernel: behind a grid-wide sum (then only the
+// barrier) CTA 0 re-does the NV sums in the reference's cell order; a second barrier hands
+// the result to every CTA.
+template <int NV>
+__device__ __forceinline__ bool step_serial(double (&v)[NV], const SerialJob (&jb)[NV],
+                                            const GridDesc &g, double *stage, double *ser_out,
+                                            unsigned &nser, double *slots,
+                                            unsigned long long *counter, unsigned int *err,
+                                            unsigned long long &gen, const int G, double *sm,
+                                            double *s_tot) {
+    double *slot = ser_out + (size_t)(nser++ & 1u) * SER_MAXJ;
+    if (blockIdx.x == 0) serial_reduce(g, jb, NV, stage, slot);
+    double z[2] = {0.0, 0.0};
+    if (!step_allsum<2>(z, slots, counter, err, ++gen, G, sm, s_tot)) return false;
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = __ldcg(slot + k);
+    return true;
+}
+
 // The loop body of solveOrder2 (P:700-742) in one cooperative launch, for grids
 // so small that a time step is a chain of launch latencies and host round trips
 // (the shipped 257 x 257 run: ~6 CG iterations per step in ~3 Picard iterates).
@@ -1560,9 +1693,12 @@ __device__ __forceinline__ bool step_allsum(double (&v)[NV], double *slots,
 // take the same decisions (CG:88-90, P:706, P:732); nothing goes through the
 // host until the step is over.  Cell arithmetic is the kernels' own
 // (stencil_tile, solve_c_cell, dfunc): only the summation order differs.
+template <bool SERIAL>
 __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
     __shared__ double sm[128];
     __shared__ double s_tot[4];
+    __shared__ double s_stage[SERIAL ? 2 * SER_MAXJ * SER_CH : 1];   // PDEODE_SUM_ORDER=serial
+    unsigned nser = 0;
     const StencilArgs &a = A.st;
     const GridDesc g = a.g;
     const NumParams np = a.np;
@@ -1660,6 +1796,10 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
         double acc[2] = {0.0, 0.0};
         stencil_tile<MODE_INIT>(a, T, V, j0, i_begin, i_end, acc[0], acc[1]);
         ok = step_allsum<2>(acc, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+        if (SERIAL && ok) {
+            const SerialJob jb[2] = {{a.r, a.r, SER_DOT, 0}, {T.x, T.x, SER_DOT, 0}};
+            ok = step_serial<2>(acc, jb, g, s_stage, A.ser_out, nser, A.slots, A.counter, err, gen, G, sm, s_tot);
+        }
         rho = acc[0]; xx = acc[1];                   // CG:53
         stamp();
     }
@@ -1678,6 +1818,10 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
             double acc[2] = {0.0, 0.0};
             stencil_tile<MODE_CG>(a, T, V, j0, i_begin, i_end, acc[0], acc[1]);
             ok = step_allsum<2>(acc, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+            if (SERIAL && ok) {                    // dotProd(p,q) (CG:76), sum(p*p) (CG:87)
+                const SerialJob jb[2] = {{T.p, a.q, SER_DOT, 0}, {T.p, T.p, SER_DOT, 0}};
+                ok = step_serial<2>(acc, jb, g, s_stage, A.ser_out, nser, A.slots, A.counter, err, gen, G, sm, s_tot);
+            }
             if (!ok) break;
             stamp();
             pq = acc[0]; pp = acc[1];
@@ -1703,6 +1847,10 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
                 }
             }
             ok = step_allsum<2>(rx, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+            if (SERIAL && ok) {                    // dotProd(r,r) (CG:59), sum(sol*sol) (CG:57)
+                const SerialJob jb[2] = {{a.r, a.r, SER_DOT, 0}, {x, x, SER_DOT, 0}};
+                ok = step_serial<2>(rx, jb, g, s_stage, A.ser_out, nser, A.slots, A.counter, err, gen, G, sm, s_tot);
+            }
             if (!ok) break;
             stamp();
             rho_old = rho; rho = rx[0]; xx = rx[1];                      // CG:56,59,57
@@ -1736,6 +1884,7 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
                 acc[1] += v1 ? fabs(mc.y - mn.y) : 0.0;
             }
         }
+        const double *const ser_Cc = A.Cb[iC], *const ser_Mc = A.Mb[iM];   // the previous iterate
         iC = icnew;                                  // C = Cnew (P:728)
         iM = inew;                                   // M = Mnew (P:729)
 
@@ -1754,6 +1903,11 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
         };
         build_next(acc[2], acc[3]);
         ok = step_allsum<4>(acc, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+        if (SERIAL && ok) {                        // calcDiff x2 (P:725-726), then CG:59,57 of the next solve
+            const SerialJob jb[4] = {{ser_Cc, A.Cb[iC], SER_ABSDIFF, 0}, {ser_Mc, A.Mb[iM], SER_ABSDIFF, 0},
+                                     {a.r, a.r, SER_DOT, 0}, {T.x, T.x, SER_DOT, 0}};
+            ok = step_serial<4>(acc, jb, g, s_stage, A.ser_out, nser, A.slots, A.counter, err, gen, G, sm, s_tot);
+        }
         if (!ok) break;
         stamp();
         diffC = acc[0] / n_glob;                     // P:961
@@ -2059,9 +2213,17 @@ static int persist_occupancy() {
         cudaGetLastError();
         return 0;
     }
+    if (cudaFuncSetAttribute(k_cg_persist<BS, PERSIST_DEPTH, false, true>,
+                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+        cudaGetLastError();
+        return 0;
+    }
     int n = 0;
     const bool want_defer = getenv("PDEODE_PERSIST_DEFER") && atoi(getenv("PDEODE_PERSIST_DEFER")) != 0;
-    cudaError_t e = want_defer
+    const bool ser = getenv("PDEODE_SUM_ORDER") && getenv("PDEODE_SUM_ORDER")[0] == 's';
+    cudaError_t e = ser
+        ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cg_persist<BS, PERSIST_DEPTH, false, true>, BS + 32, smem)
+        : want_defer
         ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cg_persist<BS, PERSIST_DEPTH, true>, BS + 32, smem)
         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_cg_persist<BS, PERSIST_DEPTH, false>, BS + 32, smem);
     if (e != cudaSuccess) {
@@ -2080,8 +2242,9 @@ static int persist_ctas_per_sm(int bs) {
 template <int BS>
 static cudaError_t launch_cg_persist_t(const PersistArgs &a, cudaStream_t st) {
     void *args[] = {const_cast<PersistArgs *>(&a)};
-    const void *fn = a.st.defer_x ? (const void *)k_cg_persist<BS, PERSIST_DEPTH, true>
-                                  : (const void *)k_cg_persist<BS, PERSIST_DEPTH, false>;
+    const void *fn = a.serial ? (const void *)k_cg_persist<BS, PERSIST_DEPTH, false, true>
+                 : a.st.defer_x ? (const void *)k_cg_persist<BS, PERSIST_DEPTH, true>
+                                : (const void *)k_cg_persist<BS, PERSIST_DEPTH, false>;
     return cudaLaunchCooperativeKernel(fn,
                                        dim3(a.nstrips * a.nchunks), dim3(BS + 32), args,
                                        Ring<BS, PERSIST_DEPTH>::BYTES, st);
@@ -2095,8 +2258,8 @@ cudaError_t launch_cg_persist(const PersistArgs &a, int BS, cudaStream_t st) {
 
 cudaError_t launch_step_persist(const StepArgs &a, int BS, cudaStream_t st) {
     void *args[] = {const_cast<StepArgs *>(&a)};
-    return cudaLaunchCooperativeKernel((const void *)k_step_persist, dim3(a.nstrips * a.nchunks),
-                                       dim3(BS), args, 0, st);
+    const void *fn = a.serial ? (const void *)k_step_persist<true> : (const void *)k_step_persist<false>;
+    return cudaLaunchCooperativeKernel(fn, dim3(a.nstrips * a.nchunks), dim3(BS), args, 0, st);
 }
 
 LaunchCfg launch_config(const GridDesc &g) {
@@ -2195,7 +2358,10 @@ LaunchCfg launch_config(const GridDesc &g) {
     c.s_nstrips = cdiv(g.P, 2 * c.s_cw);
     {
         int n = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_step_persist, c.s_BS, 0) != cudaSuccess) {
+        // sized for the serial-order instantiation too (it holds 16 KB of staging)
+        const bool ser = getenv("PDEODE_SUM_ORDER") && getenv("PDEODE_SUM_ORDER")[0] == 's';
+        if ((ser ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_step_persist<true>, c.s_BS, 0)
+                 : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, k_step_persist<false>, c.s_BS, 0)) != cudaSuccess) {
             cudaGetLastError();
             n = 0;
         }
@@ -2257,12 +2423,16 @@ template <int BS>
 static cudaError_t launch_init_bulk(const StencilArgs &a, cudaStream_t st) {
     constexpr int DEPTH = 4;
     constexpr size_t smem = Ring<BS, DEPTH>::BYTES;
-    static bool attr_set = false;
-    if (!attr_set) {
+    // the attribute is per device: one flag per device, set by whichever thread gets there
+    // first (setting it twice is harmless)
+    static std::atomic<bool> attr_set[MAX_DEVICES];
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= MAX_DEVICES || !attr_set[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(k_init_bulk<BS, DEPTH>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < MAX_DEVICES) attr_set[dev].store(true, std::memory_order_release);
     }
     dim3 grid(cdiv(a.g.P, 2 * BS), cdiv(a.g.rows, a.TR));
     k_init_bulk<BS, DEPTH><<<grid, BS + 32, smem, st>>>(a);
@@ -2281,15 +2451,17 @@ template <int BS, int DEPTH>
 static cudaError_t launch_spmv_bulk(const StencilArgs &a, cudaStream_t st) {
     constexpr int TC = 2 * BS;
     constexpr size_t smem = Ring<BS, DEPTH>::BYTES;
-    static bool attr_set = false;
-    if (!attr_set) {
+    static std::atomic<bool> attr_set[MAX_DEVICES];      // per device, see launch_init_bulk
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev < 0 || dev >= MAX_DEVICES || !attr_set[dev].load(std::memory_order_acquire)) {
         cudaError_t e = cudaFuncSetAttribute(k_spmv_bulk<BS, DEPTH, false>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         e = cudaFuncSetAttribute(k_spmv_bulk<BS, DEPTH, true>,
                                  cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        attr_set = true;
+        if (dev >= 0 && dev < MAX_DEVICES) attr_set[dev].store(true, std::memory_order_release);
     }
     dim3 grid(cdiv(a.g.P, TC), cdiv(a.g.rows, a.TR));
     if (a.defer_x) k_spmv_bulk<BS, DEPTH, true><<<grid, BS + 32, smem, st>>>(a);
@@ -2342,6 +2514,15 @@ cudaError_t launch_mass(const MassArgs &a, cudaStream_t st) {
     int nb = flat_blocks(a.n2);
     if (nb > 296) nb = 296;
     k_mass<<<nb, 256, 0, st>>>(a);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_serial_reduce(const GridDesc &g, const SerialJob *jobs, int nj, double *out,
+                                 cudaStream_t st) {
+    SerialArgs a{};
+    a.g = g; a.nj = nj < SER_MAXJ ? nj : SER_MAXJ; a.out = out;
+    for (int q = 0; q < a.nj; ++q) a.job[q] = jobs[q];
+    k_serial_reduce<<<1, 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 
