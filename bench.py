@@ -12,7 +12,15 @@ N > 1   : row slabs over N B200s (strong scaling: the grid is fixed), launched b
           torch.distributed.run, one rank per GPU; torch.distributed is used only
           to hand out the NCCL id and to take the max of the per-rank times.
 
-One JSON line is printed by rank 0.
+One JSON line is printed by rank 0.  Besides the contract's keys it carries
+  parity        (N > 1) the slabs gathered on rank 0 against the same steps on a 1-rank context:
+                relative L2 of M and C, CG and Picard totals of both; a failure exits non-zero
+  strong_16384  the north-star strong-scaling point measured in the same run: 16384 x 16384 at
+                the shipped exponents and at the stiff ones (beta = 6, height 0.95), so that
+                T1 / (N * TN) can be computed from two lines of this program
+  --impl reference times the reference's own CPU code (oracle/_ref/libref_omp.so: its Fortran
+  sources translated to C where they lie; else the oracle port) on ALL host cores: the OpenMP
+  thread count is set explicitly (torchrun exports OMP_NUM_THREADS=1).
 """
 import argparse
 import json
@@ -126,13 +134,66 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+def host_threads():
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
+
+
+def force_omp_threads():
+    """All host cores for the CPU arm, whatever the launcher exported (torch.distributed.run
+    sets OMP_NUM_THREADS=1 in every rank's environment).  Returns the thread count set."""
+    import ctypes
+    n = host_threads()
+    os.environ["OMP_NUM_THREADS"] = str(n)
+    os.environ.pop("OMP_THREAD_LIMIT", None)
+    try:
+        g = ctypes.CDLL("libgomp.so.1")      # the runtime liboracle_omp.so / libref_omp.so link to
+        g.omp_set_num_threads(n)
+        g.omp_get_max_threads.restype = ctypes.c_int
+        return int(g.omp_get_max_threads())
+    except OSError:
+        return n
+
+
+def reference_cpu(row, col, height, depth, cg_iters):
+    """The reference's own CPU code on the host cores: GenMatrixM + solveLSDIAG
+    (PDE-ODEsolver.f90:517-590, CGdiag.f90:1-95) of step 0's first Picard iterate, the solve
+    truncated to `cg_iters` iterations through its own iteration cap (CG:88).
+    oracle/_ref/libref_omp.so is the reference's Fortran translated to C where it lies (no
+    Fortran compiler in this image) and built with the flags of runAll_paral.sh:6; without it
+    the oracle port is timed.  Returns (cell-iterations/s, cores, seconds, iterations, kind)."""
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    cores = force_omp_threads()
+    ref_so = os.path.join(ROOT, "oracle", "_ref", "libref_omp.so")
+    if not os.path.exists(ref_so):
+        v, c2, dt, nit = cpu_baseline(row, col, height, depth, cg_iters)
+        return v, c2, dt, nit, "port"
+    import oracle_lib as ol
+    import ref_lib as rl
+    force_omp_threads()
+    ref = rl.Ref(omp=True)
+    cores = force_omp_threads()
+    p = ol.default_params(row)
+    M0, C0 = ic1(row, col, height, depth)
+    n = row * col
+    t0 = time.perf_counter()
+    A, ioff, rhs = ref.gen_matrix(M0, C0, row, col, p)
+    sol, nit, _, _, stop = ref.solve_ls_diag(A, ioff, np.zeros(n), rhs, cg_iters - 1, p.e1, p.e2)
+    dt = time.perf_counter() - t0
+    return n * nit / dt, cores, dt, nit, "reference"
+
+
 def cpu_baseline(row, col, height, depth, cg_iters):
     """The oracle (a port of the reference, not gfortran) on the host cores:
     the first solve of step 0 of the same workload, truncated to `cg_iters`
     CG iterations.  Returns (cell-iterations/s, cores, seconds, iterations)."""
     sys.path.insert(0, os.path.join(ROOT, "tests"))
+    force_omp_threads()
     import oracle_lib as ol
     ol.build_oracle()
+    force_omp_threads()
     p = ol.default_params(row)
     o = ol.Oracle(row, col, p, omp=True)
     M0, C0 = ic1(row, col, height, depth)
@@ -147,8 +208,8 @@ def cpu_baseline(row, col, height, depth, cg_iters):
 
 
 def run_reference(args):
-    """--impl reference: the reference's CPU algorithm (oracle port; the image has
-    no Fortran compiler) on all host cores, same config / metric / unit."""
+    """--impl reference: the reference's own CPU implementation on ALL host cores, same config /
+    metric / unit as the b200 arm."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -156,25 +217,30 @@ def run_reference(args):
     iters = args.ref_cg_iters
     vals = []
     for k in range(args.warmup + args.steps):
-        v, cores, dt, nit = cpu_baseline(row, col, args.height, args.depth, iters)
+        v, cores, dt, nit, kind = reference_cpu(row, col, args.height, args.depth, iters)
         if k >= args.warmup:
             vals.append((v, dt, nit))
     tot_it = sum(n for _, _, n in vals)
     tot_t = sum(t for _, t, _ in vals)
     value = row * col * tot_it / tot_t
+    what = ("GenMatrixM + solveLSDIAG of the reference (its .f90 sources translated to C by "
+            "oracle/f90c and built with -O3 -fopenmp, as runAll_paral.sh:6)" if kind == "reference"
+            else "the oracle port of GenMatrixM + CGdiag.f90 (OpenMP)")
     sample = (f"each step = operator assembly + the first {iters} CG iterations of step 0's first "
-              f"solve on the same {row}x{col} IC-1 grid (oracle port of CGdiag.f90, OpenMP)")
+              f"solve on the same {row}x{col} IC-1 grid: {what}")
     out = {
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT,
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * tot_t / max(1, args.steps), "higher_is_better": True,
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, 1),
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port",
-                         "sample": sample},
+        "config": workload_config(args, max(1, args.gpus)),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind,
+                         "sample": sample, "host_cores": host_threads()},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
+    if cores == 1 and host_threads() > 1:
+        out["cpu_baseline"]["warning"] = "ran on one thread of a multi-core host"
     emit(out)
 
 
@@ -226,6 +292,11 @@ def main():
     ap.add_argument("--cg-cap", type=int, default=100000)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-strong16384", action="store_true",
+                    help="skip the 16384^2 strong-scaling sub-record")
+    ap.add_argument("--strong-cg-cap", type=int, default=600,
+                    help="CG iterations per step of the stiff 16384^2 sub-record")
+    ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the check against one rank")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                      # timing rule: W >= 3
@@ -234,6 +305,8 @@ def main():
         run_reference(args)
         return
 
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1:
+        force_omp_threads()                  # the cpu_baseline leg below uses all host cores
     import torch
     import pdeode_b200 as pb
 
@@ -244,15 +317,21 @@ def main():
         raise SystemExit("bench.py: no CUDA device; the product path has no CPU fallback")
     torch.cuda.set_device(local)
     dist = None
-    nccl_id = None
     if world > 1:
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def fresh_nccl_id():
+        """One NCCL id per multi-rank context, made on rank 0 and handed out with torch.distributed."""
+        if world == 1:
+            return None
         idt = torch.zeros(pb.NCCL_ID_BYTES, dtype=torch.uint8, device="cuda")
         if rank == 0:
             idt.copy_(torch.frombuffer(bytearray(pb.nccl_unique_id()), dtype=torch.uint8))
         dist.broadcast(idt, 0)
-        nccl_id = bytes(idt.cpu().numpy().tobytes())
+        return bytes(idt.cpu().numpy().tobytes())
+
+    nccl_id = fresh_nccl_id()
 
     row = col = args.grid
     n = row * col
@@ -292,14 +371,18 @@ def main():
     # ---- resident-state throughput (inputs already in HBM) ----
     s.set_state_ptr(Mh.data_ptr(), Ch.data_ptr())
 
+    pic_total = [0]
+
     def resident_step():
         r = s.step()
         if r["rc"] != 0:
             raise SystemExit(f"bench.py: pdeode_step returned {r['rc']} (CG cap or Picard cap hit)")
+        pic_total[0] += r["countIters"]
         return r["nitSum"]
 
+    it_warm = 0
     for _ in range(args.warmup):
-        resident_step()
+        it_warm += resident_step()
     l0 = s.launch_count()
     clk = ClockSampler(local)
     if rank == 0:
@@ -308,6 +391,41 @@ def main():
     clocks = clk.stop() if rank == 0 else None
     launches = s.launch_count() - l0
     value = n * it_res / t_res
+
+    # ---- N > 1: the slabs, gathered on rank 0, against the same steps on ONE rank ----
+    parity = None
+    if world > 1 and not args.no_parity:
+        nsteps_done = args.warmup + args.steps
+        Ml = np.empty(s.n_local); Cl = np.empty(s.n_local)
+        s.get_state(Ml, Cl)
+        tot = torch.tensor([it_warm + it_res, pic_total[0]], device="cuda", dtype=torch.float64)
+        gathered = [None] * world if rank == 0 else None
+        dist.gather_object((s.row0, Ml, Cl), gathered, dst=0)
+        if rank == 0:
+            gathered.sort(key=lambda t: t[0])
+            Mn = np.concatenate([g[1] for g in gathered]); Cn = np.concatenate([g[2] for g in gathered])
+            one = pb.Solver(row, col, params, device=local)
+            one.set_maxit(args.cg_cap)
+            M1, C1 = ic1(row, col, args.height, args.depth)
+            one.set_state(M1, C1)
+            it1 = pic1 = 0
+            for _ in range(nsteps_done):
+                r = one.step()
+                it1 += r["nitSum"]; pic1 += r["countIters"]
+            M1, C1 = one.get_state()
+            one.close()
+            eM = float(np.linalg.norm(Mn - M1) / np.linalg.norm(M1))
+            eC = float(np.linalg.norm(Cn - C1) / np.linalg.norm(C1))
+            itN, picN = int(tot[0].item()), int(tot[1].item())
+            # the summation order differs between N ranks and one (rank order on top of the CTA
+            # order), so CG counts may move by a few per solve and the fields by one CG step
+            # (20 e2), as between the reference's own serial and OpenMP builds; Picard is exact
+            ok = (picN == pic1 and abs(itN - it1) <= 2 * pic1 and eM <= 20 * params.e2 and eC <= 20 * params.e2)
+            parity = {"ok": bool(ok), "steps": nsteps_done, "relL2_M": eM, "relL2_C": eC,
+                      "cg_iterations": [itN, it1], "picard_iterates": [picN, pic1],
+                      "bar": "Picard exact, |dCG| <= 2 per solve, relL2 <= 20*e2 = %.1e" % (20 * params.e2),
+                      "against": "the same %d steps on a 1-rank context on rank 0's GPU" % nsteps_done}
+        barrier()
 
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
@@ -318,7 +436,8 @@ def main():
             s.get_state_ptr(Mout.data_ptr(), Cout.data_ptr())  # D2H of the result
             s.mass()
             return k
-        e2e_step()
+        for _ in range(3):
+            e2e_step()
         t_e, it_e = timed(e2e_step, args.steps)
         e2e = {"value": n * it_e / t_e, "unit": UNIT,
                "h2d_bytes_per_step": 2 * 8 * n, "d2h_bytes_per_step": 2 * 8 * n + 16,
@@ -371,22 +490,64 @@ def main():
                     "GBps": 96 * n / (ks["cg_spmv"]["ms"] + ks["cg_update"]["ms"]) / 1e6,
                     "frac": 96 * n / (ks["cg_spmv"]["ms"] + ks["cg_update"]["ms"]) / 1e6 / peak}}
     s.close()
+    del Mh, Ch, Mout, Cout
+
+    # ---- the north-star strong-scaling point, in the same run: 16384 x 16384 over `world` GPUs ----
+    strong = None
+    if not args.no_strong16384:
+        strong = {"grid": [16384, 16384], "n_gpus": world, "unit": UNIT,
+                  "note": "strong scaling: the same grid and the same CG iterations at every N; "
+                          "efficiency(N) = value(N) / (N * value(1)) from two lines of this program"}
+        g16 = 16384
+        n16 = g16 * g16
+        runs = (
+            # shipped exponents, IC 1 with height 0.9: whole steps (about 2000 CG iterations each)
+            ("shipped_beta4", dict(), 0.9, None, 3, 3),
+            # SURVEY config 4, the stiff regime of README.md:42-44 / P:471: beta = 6, height 0.95.
+            # Its solves run for 1e4 .. 1e6 iterations, so a step is cut to its first Picard
+            # iterate (eSoln above the residual sum, P:706) and --strong-cg-cap CG iterations
+            # (CG:88): the same iterations at every N
+            ("stiff_beta6", dict(beta=6, eSoln=1.5), 0.95, args.strong_cg_cap, 3, 3),
+        )
+        for name, over, height, cap, w16, k16 in runs:
+            p16 = pb.default_params(g16, **over)
+            s16 = pb.Solver(g16, g16, p16, device=local, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
+            s16.set_stream(stream.cuda_stream)
+            s16.set_maxit(cap if cap is not None else 10 * args.cg_cap)
+            s16.set_initial_condition(1, args.depth, height)      # built on the device (P:279-288)
+            for _ in range(w16):
+                s16.step()
+            clk16 = ClockSampler(local)
+            if rank == 0:
+                clk16.start()
+            t16, it16 = timed(lambda: s16.step()["nitSum"], k16)
+            c16 = clk16.stop() if rank == 0 else None
+            mM, mC = s16.mass()
+            strong[name] = {"value": n16 * it16 / t16, "ms_per_step": 1e3 * t16 / k16, "steps": k16,
+                            "warmup": w16, "cg_iterations": it16, "clocks": c16,
+                            "params": dict(over, height=height, cg_cap_per_solve=cap),
+                            "mean_M": mM, "mean_C": mC, "engine": s16.engine_info(),
+                            "exchange": s16.exchange_mode()}
+            if not (np.isfinite(mM) and np.isfinite(mC)):
+                strong[name]["invalid"] = "non-finite state"
+            s16.close()
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, cores, dt, nit = cpu_baseline(row, col, args.height, args.depth, args.cpu_cg_iters)
-        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": "port",
+        v, cores, dt, nit, kind = reference_cpu(row, col, args.height, args.depth, args.cpu_cg_iters)
+        cpu = {"value": v, "unit": UNIT, "cores": cores, "kind": kind, "host_cores": host_threads(),
                "sample": f"operator assembly + first {nit} CG iterations of step 0's first solve, same "
-                         f"{row}x{col} grid and IC, oracle port with OpenMP ({dt:.1f} s)"}
+                         f"{row}x{col} grid and IC ({dt:.1f} s): " +
+                         ("the reference's GenMatrixM + solveLSDIAG (its .f90 translated to C by oracle/f90c, "
+                          "-O3 -fopenmp as runAll_paral.sh:6)" if kind == "reference" else
+                          "oracle port with OpenMP")}
 
     if rank == 0:
-        cfg = workload_config(args, world)
-        cfg["exchange"] = {"single": "none (one GPU)",
-                           "nccl": "NCCL send/recv of one ghost row + 2 all-reduces per CG iteration",
-                           "peer": "inside K_A/K_B over NVLink peer memory (CUDA IPC): ghost rows and "
-                                   "dot-product slots written straight into the other GPUs"}[exchange]
-        if default_ms:
-            cfg["shipped_parameters_run"] = default_ms
+        cfg = workload_config(args, world)         # the same dict the reference arm prints
+        exchange_txt = {"single": "none (one GPU)",
+                        "nccl": "NCCL send/recv of one ghost row + 2 all-reduces per CG iteration",
+                        "peer": "inside K_A/K_B over NVLink peer memory (CUDA IPC): ghost rows and "
+                                "dot-product slots written straight into the other GPUs"}[exchange]
         out = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_res / args.steps,
@@ -394,11 +555,15 @@ def main():
             "dtype": "f64", "data": "synthetic", "config": cfg,
             "cg_iterations": it_res, "clocks": clocks, "e2e": e2e,
             "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu,
+            "exchange": exchange_txt, "shipped_parameters_run": default_ms,
+            "parity": parity, "strong_16384": strong,
         }
         emit(out)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+    if rank == 0 and parity is not None and not parity["ok"]:
+        raise SystemExit("bench.py: the %d-rank run does not match one rank: %r" % (world, parity))
 
 
 if __name__ == "__main__":

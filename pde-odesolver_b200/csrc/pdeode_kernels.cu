@@ -1901,12 +1901,25 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
             V.a = T.x0; V.b = nullptr; V.first = true; V.beta = 0.0;
             stencil_tile<MODE_INIT>(a, T, V, j0, i_begin, i_end, s0, s1);
         };
+        // serial-order verification: calcDiff x2 (P:725-726) in cell order NOW -- build_next
+        // below overwrites the buffer of the previous iterate (it becomes the next solve's target)
+        double dser[2] = {0.0, 0.0};
+        if (SERIAL) {
+            double z[2] = {0.0, 0.0};
+            ok = step_allsum<2>(z, A.slots, A.counter, err, ++gen, G, sm, s_tot);   // every CTA's Cnew is there
+            if (ok) {
+                const SerialJob jb[2] = {{ser_Cc, A.Cb[iC], SER_ABSDIFF, 0}, {ser_Mc, A.Mb[iM], SER_ABSDIFF, 0}};
+                ok = step_serial<2>(dser, jb, g, s_stage, A.ser_out, nser, A.slots, A.counter, err, gen, G, sm, s_tot);
+            }
+            if (!ok) break;
+        }
         build_next(acc[2], acc[3]);
         ok = step_allsum<4>(acc, A.slots, A.counter, err, ++gen, G, sm, s_tot);
-        if (SERIAL && ok) {                        // calcDiff x2 (P:725-726), then CG:59,57 of the next solve
-            const SerialJob jb[4] = {{ser_Cc, A.Cb[iC], SER_ABSDIFF, 0}, {ser_Mc, A.Mb[iM], SER_ABSDIFF, 0},
-                                     {a.r, a.r, SER_DOT, 0}, {T.x, T.x, SER_DOT, 0}};
-            ok = step_serial<4>(acc, jb, g, s_stage, A.ser_out, nser, A.slots, A.counter, err, gen, G, sm, s_tot);
+        if (SERIAL && ok) {                          // CG:59,57 of the next solve
+            const SerialJob jb[2] = {{a.r, a.r, SER_DOT, 0}, {T.x, T.x, SER_DOT, 0}};
+            double nx[2] = {0.0, 0.0};
+            ok = step_serial<2>(nx, jb, g, s_stage, A.ser_out, nser, A.slots, A.counter, err, gen, G, sm, s_tot);
+            acc[0] = dser[0]; acc[1] = dser[1]; acc[2] = nx[0]; acc[3] = nx[1];
         }
         if (!ok) break;
         stamp();
