@@ -76,6 +76,16 @@ int pdeode_create_dist(pdeode_ctx **ctx, int row, int col,
                        int nranks, const void *id);
 int pdeode_nccl_unique_id(void *id_out);
 
+/* The same row-slab solve on ngpus devices of ONE process: the reference's drivers start a
+ * single process (`echo FILE | ./a.out`, runAll.sh:7, twoDimension_runall.sh:7), so this is the
+ * form the drop-in solver uses for grids larger than one GPU (PDEODE_NGPUS).  The context it
+ * returns is used with every other entry point exactly like a single-GPU one -- fields are the
+ * whole grid, counts are the step's -- while inside one worker thread per GPU drives a slab
+ * context; the slabs see each other's memory through peer access (NVLink) instead of CUDA IPC.
+ * devices: ngpus distinct CUDA ordinals, or NULL for 0 .. ngpus-1.  ngpus = 1 is pdeode_create. */
+int pdeode_create_group(pdeode_ctx **ctx, int row, int col, const pdeode_params *p,
+                        int ngpus, const int *devices);
+
 int pdeode_destroy(pdeode_ctx *ctx);
 
 /* Number of CUDA devices this process can use (0 and PDEODE_ERR_NODEVICE if none). */

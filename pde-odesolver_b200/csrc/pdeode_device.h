@@ -59,7 +59,11 @@ struct DevScal {
     // tickets for the last-block-done reductions
     unsigned int ticket[8];
     int error;           // 1: a peer exchange timed out (multi-rank peer mode)
-    int pad2;
+    // one rank, kernel-per-phase engine: the update kernel of the LAST iteration does nothing
+    // (its r is dead; CG:81) and leaves sol += alfa p (CG:80) to the C-update kernel that reads
+    // sol anyway: tail = 1 until k_solvec has applied it
+    int tail;
+    long long solvec_seq; // StencilArgs::seq of the solve whose C update has run
 };
 
 // How a kernel's reduction leaves the grid (StencilArgs / UpdateArgs ::fuse_scalars).
@@ -163,6 +167,8 @@ struct StepOut {
     int iM, iC, iMnew, ip;               // buffer roles after the step
     unsigned long long gen;              // generation of the last grid-wide sum (see step_allsum)
     unsigned long long seq;              // StepArgs::seq, stored last: the report is complete
+    double sumM, sumC;                   // field sums of the final state (calcMass, P:783-787)
+    int have_sums, pad1;
     int nstamps, pad;                    // PDEODE_STEP_STAMPS=1: phase time stamps of CTA 0
     unsigned long long stamp_ns[48], stamp_clk[48];
 };
@@ -204,6 +210,7 @@ struct UpdateArgs {
     int fuse_scalars;
     int reverse;           // 1: sweep high -> low addresses (L2 reuse against the SpMV kernel)
     int r_only;            // 1: x is updated by the next SpMV kernel (88-byte iteration)
+    int tail_ok;           // 1: the last iteration's update may be left to k_solvec (DevScal::tail)
     long long seq;
     NumParams np;          // SUMS_PEER: the stop test runs in this kernel's last CTA
     double *trace;
@@ -215,9 +222,13 @@ struct SolveCArgs {
     GridDesc g;
     NumParams np;
     DevScal *S;
-    double *partials;
-    const double *Mprev, *Mnew, *Cprev, *Ccur, *Mcur;
+    double *partials;      // [4][blocks]
+    const double *Mprev, *Cprev, *Ccur, *Mcur;
+    double *Mnew;          // CG solution; written here only when DevScal::tail is pending
     double *Cnew;
+    const double *pbuf[2]; // the CG directions; the last one is pbuf[ip0 ^ (nit & 1)]
+    int ip0;
+    int gated;             // 1: return unless the solve has finished and this C update has not run
     long long n2;
     int fuse_scalars;
     long long seq;

@@ -12,6 +12,11 @@
 
 #include <algorithm>
 #include <atomic>
+#include <condition_variable>
+#include <functional>
+#include <memory>
+#include <mutex>
+#include <thread>
 #include <sched.h>
 #include <cstdio>
 #include <cstdlib>
@@ -32,7 +37,14 @@ struct Snapshot { DevScal s; };
 
 }  // namespace
 
+struct pdeode_group;
+namespace { struct GroupShared; }
+
 struct pdeode_ctx {
+    // an in-process group of row-slab contexts (pdeode_create_group): this object is then only
+    // the handle; every entry point fans out to the members, one worker thread per GPU
+    pdeode_group *group = nullptr;
+    GroupShared *gs = nullptr;    // member of an in-process group: where the peers' pointers are
     int device = 0;
     int rank = 0, nranks = 1;
     GridDesc g{};
@@ -100,6 +112,11 @@ struct pdeode_ctx {
     long long seq = 0;
     long long launches = 0;
     bool mass_valid = false;
+    // calcMass of the current state came with the step's last C update (k_solvec / the
+    // whole-step launch): pdeode_mass needs no pass of its own
+    bool sums_valid = false;
+    double sumM = 0.0, sumC = 0.0;
+    bool fuse_tail = true;        // PDEODE_FUSE_TAIL=0: the last update kernel of a solve runs in full
 
     // last step trace
     long long nit_trace[MAX_PICARD_TRACE];
@@ -248,6 +265,7 @@ int cg_iteration(pdeode_ctx *c, double *x) {
     u.wait_phase = c->phase;                 // posted by the K_A just launched
     u.post_phase = ++c->phase;
     u.r_only = defer ? 1 : 0;                        // 88-byte iteration: r only
+    u.tail_ok = (mode == SUMS_FUSED && c->fuse_tail) ? 1 : 0;
     if (defer && mode == SUMS_FUSED) CK(launch_update_r(u, c->stream));
     else CK(launch_update(u, c->stream));
     c->launches++;
@@ -267,9 +285,13 @@ int cg_iteration(pdeode_ctx *c, double *x) {
 }
 
 // GenMatrixM's centre diagonal + solveLSDIAG (P:712-714): x0 -> x.
+// sc: the C update of this Picard iterate (k_solvec, gated on the device: it runs once, as soon
+// as the solve has finished) is queued behind every chunk of CG iterations, so that ONE record
+// tells the host the iteration count and the Picard residuals; *solvec_done says whether it ran.
 int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *nit_out,
-          int *stop_out) {
+          int *stop_out, SolveCArgs *sc, bool *solvec_done) {
     c->seq++;
+    *solvec_done = false;
     if (multi(c)) {
         int rc = halo_exchange(c, const_cast<double *>(x0));
         if (rc) return rc;
@@ -332,12 +354,21 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     int chunk = (int)std::min<long long>(pred, 2048);
     bool have_pending = false;
     int pending_slot = 0;
+    const bool with_solvec = sc && sums_mode(c) == SUMS_FUSED && c->fuse_tail;
+    if (with_solvec) {
+        sc->seq = c->seq; sc->gated = 1; sc->ip0 = ip0;
+        sc->pbuf[0] = c->pbuf[0]; sc->pbuf[1] = c->pbuf[1];
+    }
     for (;;) {
         for (int k = 0; k < chunk; ++k) {
             int rc = cg_iteration(c, x);
             if (rc) return rc;
         }
         launched += chunk;
+        if (with_solvec) {
+            CK(launch_solvec(*sc, c->stream));       // P:717, P:725-726; no-op until the solve is over
+            c->launches++;
+        }
         int rc = snapshot(c, slot);
         if (rc) return rc;
         if (have_pending) {
@@ -364,7 +395,8 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         if (c->snap[slot].s.finished) break;
         chunk = (int)std::min<long long>(std::max<long long>(2, launched / 2), 1024);
     }
-    const DevScal &fin = c->snap[slot].s;
+    if (slot != 0) c->snap[0] = c->snap[slot];       // callers read the final record in slot 0
+    const DevScal &fin = c->snap[0].s;
     if (fin.error) {
         c->err = multi(c) ? "peer exchange timed out (a rank stopped posting)"
                           : "grid barrier of the persistent solve timed out";
@@ -374,7 +406,8 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
     // iteration sits in the buffer given by the parity of nit
     c->ip = ip0 ^ (int)(fin.nit & 1);
     c->p = c->pbuf[c->ip];
-    if (c->solve_defer) {
+    *solvec_done = with_solvec;
+    if (c->solve_defer && !with_solvec) {
         // the x update of the last iteration was deferred to a kernel that never ran
         CK(launch_xtail(x, c->p, c->S, (long long)c->g.rows * c->g.P / 2, c->stream));
         c->launches++;
@@ -537,8 +570,89 @@ int setup_peer(pdeode_ctx *c) {
     return PDEODE_OK;
 }
 
+// What the members of an in-process group (pdeode_create_group) tell each other at create
+// time, and the barrier they meet at.
+struct GroupShared {
+    int n = 0;
+    std::mutex mu;
+    std::condition_variable cv;
+    int arrived = 0;
+    unsigned long long gen = 0;
+    void *comm_block[PEER_MAX_RANKS] = {nullptr};
+    double *r_base[PEER_MAX_RANKS] = {nullptr};
+    int rows[PEER_MAX_RANKS] = {0};
+    int device[PEER_MAX_RANKS] = {0};
+    int ok[PEER_MAX_RANKS] = {0};
+    bool dead = false;            // a member failed before reaching a barrier: nobody waits any more
+    void barrier() {
+        std::unique_lock<std::mutex> lk(mu);
+        if (dead) return;
+        const unsigned long long g0 = gen;
+        if (++arrived == n) { arrived = 0; ++gen; cv.notify_all(); return; }
+        cv.wait(lk, [&] { return gen != g0 || dead; });
+    }
+    void abandon() {
+        std::lock_guard<std::mutex> lk(mu);
+        dead = true;
+        cv.notify_all();
+    }
+};
+
+// setup_peer for ranks living in ONE process (one worker thread per GPU): no IPC handles --
+// cudaIpcOpenMemHandle refuses handles of the own process -- but plain peer access to the
+// other devices and the members' raw device pointers.
+int setup_peer_inproc(pdeode_ctx *c) {
+    GroupShared *gs = c->gs;
+    const int nr = c->nranks;
+    const size_t slots_bytes = sizeof(double) * PEER_SLOTS * PEER_MAX_RANKS * PEER_VALS;
+    const size_t flags_bytes = sizeof(unsigned long long) * PEER_SLOTS * PEER_MAX_RANKS;
+    cudaError_t e = cudaMalloc(&c->comm_block, slots_bytes + flags_bytes);
+    if (e == cudaSuccess) e = cudaMemset(c->comm_block, 0, slots_bytes + flags_bytes);
+    if (e != cudaSuccess) { gs->abandon(); return fail_cuda(c, e, "comm block"); }
+    gs->comm_block[c->rank] = c->comm_block;
+    gs->r_base[c->rank] = c->base[8];
+    gs->rows[c->rank] = c->g.rows;
+    gs->device[c->rank] = c->device;
+    gs->barrier();
+    if (gs->dead) { c->err = "another member of the group failed to initialise"; return PDEODE_ERR_CUDA; }
+    bool ok = true;
+    for (int r = 0; r < nr && ok; ++r) {
+        if (r == c->rank) continue;
+        int can = 0;
+        if (cudaDeviceCanAccessPeer(&can, c->device, gs->device[r]) != cudaSuccess || !can) { ok = false; break; }
+        e = cudaDeviceEnablePeerAccess(gs->device[r], 0);
+        if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) ok = false;
+        cudaGetLastError();
+    }
+    gs->ok[c->rank] = ok ? 1 : 0;
+    gs->barrier();
+    if (gs->dead) { c->err = "another member of the group failed to initialise"; return PDEODE_ERR_CUDA; }
+    for (int r = 0; r < nr; ++r) ok = ok && gs->ok[r];
+    if (ok) {
+        PeerComm pc{};
+        pc.rank = c->rank; pc.nranks = nr;
+        double ms = 10000.0;
+        if (const char *t = getenv("PDEODE_PEER_TIMEOUT_MS")) { const double v = atof(t); if (v > 0) ms = v; }
+        pc.timeout_clocks = (long long)(ms * 2.0e6);
+        pc.slots = (const double *)c->comm_block;
+        pc.flags = (const unsigned long long *)((char *)c->comm_block + slots_bytes);
+        const size_t origin = (size_t)GUARD + (size_t)c->g.P;
+        for (int r = 0; r < nr; ++r) {
+            pc.peer_slots[r] = (double *)gs->comm_block[r];
+            pc.peer_flags[r] = (unsigned long long *)((char *)gs->comm_block[r] + slots_bytes);
+        }
+        if (c->rank > 0) { pc.r_up = gs->r_base[c->rank - 1] + origin; pc.rows_up = gs->rows[c->rank - 1]; }
+        if (c->rank < nr - 1) pc.r_dn = gs->r_base[c->rank + 1] + origin;
+        c->pc = pc;
+        c->peer = true;
+    } else {
+        c->err = "peer access between the group's devices unavailable; using the NCCL exchange";
+    }
+    return PDEODE_OK;
+}
+
 int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int device, int rank,
-                int nranks, const void *id) {
+                int nranks, const void *id, GroupShared *gs = nullptr) {
     if (!out) return PDEODE_ERR_ARG;
     *out = nullptr;
     if (!p || row < 3 || col < 2 || nranks < 1 || rank < 0 || rank >= nranks ||
@@ -552,6 +666,7 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     if (!c) return PDEODE_ERR_NOMEM;
     *out = c;   // returned even on failure so that pdeode_last_error works; destroy it
     c->device = device; c->rank = rank; c->nranks = nranks; c->params = *p;
+    c->gs = gs;
     CK(cudaSetDevice(device));
 
     int r0 = 0, nrows_local = 0;
@@ -580,6 +695,7 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
     c->pbuf[0] = origin(9); c->pbuf[1] = origin(11); c->ip = 0; c->p = c->pbuf[0];
 
     c->cfg = launch_config(c->g);
+    if (const char *ft = getenv("PDEODE_FUSE_TAIL")) c->fuse_tail = atoi(ft) != 0;
     if (const char *so = getenv("PDEODE_SUM_ORDER")) {
         if (strcmp(so, "serial") == 0) {
             if (nranks > 1) { c->err = "PDEODE_SUM_ORDER=serial is a one-rank verification mode"; return PDEODE_ERR_ARG; }
@@ -637,16 +753,158 @@ int create_impl(pdeode_ctx **out, int row, int col, const pdeode_params *p, int 
         if (!nccl().ok) { c->err = "libnccl.so.2 not found"; return PDEODE_ERR_NCCL; }
         ncclUniqueId uid;
         memcpy(&uid, id, sizeof uid);
+        if (gs) {
+            // in-process group: nobody enters the (blocking) communicator setup unless every
+            // member got this far
+            gs->barrier();
+            if (gs->dead) { c->err = "another member of the group failed to initialise"; return PDEODE_ERR_CUDA; }
+        }
         NK(nccl().CommInitRank(&c->comm, nranks, uid, rank));
         CK(cudaMalloc(&c->gather, sizeof(double) * 8 * (size_t)nranks));
         const char *pe = getenv("PDEODE_PEER");
         if (!(pe && pe[0] == '0') && nranks <= PEER_MAX_RANKS && c->cfg.variant == 1) {
-            int rc = setup_peer(c);
+            // ranks of one process see each other's memory through peer access; ranks in
+            // separate processes through CUDA-IPC mappings
+            int rc = gs ? setup_peer_inproc(c) : setup_peer(c);
             if (rc) return rc;
         }
     }
     return PDEODE_OK;
 }
+
+// ---------------------------------------------------------------- in-process multi-GPU group
+
+// One worker thread per member: every entry point of a group context runs on all members at
+// once (their kernels wait for each other across GPUs, so they must be launched together).
+struct Worker {
+    std::thread th;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has = false, quit = false;
+    Worker() {
+        th = std::thread([this] {
+            for (;;) {
+                std::function<void()> j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [&] { return has || quit; });
+                    if (quit && !has) return;
+                    j = std::move(job);
+                }
+                j();
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    has = false;
+                }
+                cv.notify_all();
+            }
+        });
+    }
+    void post(std::function<void()> j) {
+        std::lock_guard<std::mutex> lk(mu);
+        job = std::move(j);
+        has = true;
+        cv.notify_all();
+    }
+    void wait() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [&] { return !has; });
+    }
+    ~Worker() {
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        if (th.joinable()) th.join();
+    }
+};
+
+}  // namespace
+
+struct pdeode_group {
+    int n = 0;
+    std::vector<pdeode_ctx *> m;
+    std::vector<std::unique_ptr<Worker>> w;
+    GroupShared sh;
+};
+
+namespace {
+
+// f(k, member) on every member at once; returns the first error, else member 0's code
+// (warnings included).
+template <class F>
+int group_run(pdeode_ctx *front, F f) {
+    pdeode_group *G = front->group;
+    std::vector<int> rc((size_t)G->n, 0);
+    for (int k = 0; k < G->n; ++k) G->w[(size_t)k]->post([&, k] { rc[(size_t)k] = f(k, G->m[(size_t)k]); });
+    for (int k = 0; k < G->n; ++k) G->w[(size_t)k]->wait();
+    for (int k = 0; k < G->n; ++k)
+        if (rc[(size_t)k] & PDEODE_ERR_MASK) {
+            front->err = "GPU " + std::to_string(k) + ": " + (G->m[(size_t)k] ? G->m[(size_t)k]->err : std::string("?"));
+            return rc[(size_t)k];
+        }
+    return rc[0];
+}
+
+int group_create(pdeode_ctx **out, int row, int col, const pdeode_params *p, int ngpus,
+                 const int *devices) {
+    if (!out) return PDEODE_ERR_ARG;
+    *out = nullptr;
+    if (!p || ngpus < 1 || ngpus > PEER_MAX_RANKS || row / ngpus < 2) return PDEODE_ERR_ARG;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev <= 0) { cudaGetLastError(); return PDEODE_ERR_NODEVICE; }
+    std::vector<int> dev((size_t)ngpus);
+    for (int k = 0; k < ngpus; ++k) {
+        dev[(size_t)k] = devices ? devices[k] : k;
+        if (dev[(size_t)k] < 0 || dev[(size_t)k] >= ndev) return PDEODE_ERR_ARG;
+        for (int j = 0; j < k; ++j)
+            if (dev[(size_t)j] == dev[(size_t)k]) return PDEODE_ERR_ARG;   // slabs sharing a GPU would wait for each other forever
+    }
+    if (ngpus == 1) return create_impl(out, row, col, p, dev[0], 0, 1, nullptr);
+    if (!nccl().ok) return PDEODE_ERR_NCCL;
+    ncclUniqueId uid;
+    if (nccl().GetUniqueId(&uid) != NCCL_SUCCESS) return PDEODE_ERR_NCCL;
+    pdeode_ctx *front = new (std::nothrow) pdeode_ctx();
+    if (!front) return PDEODE_ERR_NOMEM;
+    *out = front;
+    front->group = new pdeode_group();
+    pdeode_group *G = front->group;
+    G->n = ngpus;
+    G->sh.n = ngpus;
+    G->m.assign((size_t)ngpus, nullptr);
+    for (int k = 0; k < ngpus; ++k) G->w.emplace_back(new Worker());
+    front->device = dev[0]; front->rank = 0; front->nranks = ngpus; front->params = *p;
+    front->g.rows = row; front->g.col = col; front->g.P = (col + 15) / 16 * 16;
+    front->g.row0 = 0; front->g.grow = row; front->g.n_glob = (double)((long long)row * col);
+    front->n_local = (long long)row * col;
+    const int rc = group_run(front, [&](int k, pdeode_ctx *) {
+        const int r = create_impl(&G->m[(size_t)k], row, col, p, dev[(size_t)k], k, ngpus, &uid, &G->sh);
+        if (r) G->sh.abandon();
+        return r;
+    });
+    return rc;
+}
+
+int group_destroy(pdeode_ctx *front) {
+    pdeode_group *G = front->group;
+    // collective inside (no member frees memory a peer may still write into): all at once
+    group_run(front, [&](int, pdeode_ctx *m) { return m ? pdeode_destroy(m) : 0; });
+    G->w.clear();
+    delete G;
+    delete front;
+    return PDEODE_OK;
+}
+
+// rows of the whole grid a frame contains, per member, in member order
+void group_frame_rows(pdeode_ctx *front, int filter, std::vector<int> &nro, int *nco) {
+    pdeode_group *G = front->group;
+    nro.assign((size_t)G->n, 0);
+    for (int k = 0; k < G->n; ++k) pdeode_frame_size(G->m[(size_t)k], filter, &nro[(size_t)k], nco);
+}
+
+#define GROUP(c, expr) do { if ((c) && (c)->group) return (expr); } while (0)
 
 }  // namespace
 
@@ -688,8 +946,14 @@ int pdeode_create_dist(pdeode_ctx **ctx, int row, int col, const pdeode_params *
     return create_impl(ctx, row, col, p, device, rank, nranks, id);
 }
 
+int pdeode_create_group(pdeode_ctx **ctx, int row, int col, const pdeode_params *p, int ngpus,
+                        const int *devices) {
+    return group_create(ctx, row, col, p, ngpus, devices);
+}
+
 int pdeode_destroy(pdeode_ctx *c) {
     if (!c) return PDEODE_OK;
+    GROUP(c, group_destroy(c));
     cudaSetDevice(c->device);
     if (c->stream) cudaStreamSynchronize(c->stream);
     if (c->peer && c->comm && c->gather) {
@@ -744,6 +1008,7 @@ int pdeode_slab_rows(int row, int nranks, int rank, int *row0, int *nrows) {
 
 int pdeode_local_rows(const pdeode_ctx *c, int *row0, int *nrows) {
     if (!c) return PDEODE_ERR_ARG;
+    // (a group context owns the whole grid: the fields below describe it)
     if (row0) *row0 = c->g.row0;
     if (nrows) *nrows = c->g.rows;
     return PDEODE_OK;
@@ -751,6 +1016,7 @@ int pdeode_local_rows(const pdeode_ctx *c, int *row0, int *nrows) {
 
 int pdeode_set_stream(pdeode_ctx *c, void *cuda_stream) {
     if (!c) return PDEODE_ERR_ARG;
+    if (c->group) return PDEODE_ERR_ARG;             // one stream cannot serve several devices
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     c->stream = cuda_stream ? (cudaStream_t)cuda_stream : c->own_stream;
@@ -759,6 +1025,10 @@ int pdeode_set_stream(pdeode_ctx *c, void *cuda_stream) {
 
 int pdeode_set_state(pdeode_ctx *c, const double *M, const double *C) {
     if (!c || !M || !C) return PDEODE_ERR_ARG;
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) {
+        const size_t off = (size_t)m->g.row0 * (size_t)m->g.col;
+        return pdeode_set_state(m, M + off, C + off);
+    }));
     CK(cudaSetDevice(c->device));
     c->iM = c->iMprev = 0; c->iC = c->iCprev = 0; c->iMnew = 1;
     int rc;
@@ -766,13 +1036,16 @@ int pdeode_set_state(pdeode_ctx *c, const double *M, const double *C) {
     if ((rc = upload(c, c->Cb[0], C))) return rc;
     if ((rc = zero_array(c, 1))) return rc;     // Mnew := 0, the first warm start (D8)
     c->warm = false;
-    c->mass_valid = false;
+    c->mass_valid = false; c->sums_valid = false;
     CK(cudaStreamSynchronize(c->stream));
     return PDEODE_OK;
 }
 
 int pdeode_set_initial_condition(pdeode_ctx *c, int ic, double depth, double height, int npts,
                                  const double *px, const double *py) {
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) {
+        return pdeode_set_initial_condition(m, ic, depth, height, npts, px, py);
+    }));
     if (!c || ic < 1 || ic > 10 || ic == 7) return PDEODE_ERR_ARG;
     const bool pts = (ic == 4 || ic == 5 || ic == 9 || ic == 10);
     if (pts && (npts < 0 || (npts > 0 && (!px || !py)))) return PDEODE_ERR_ARG;
@@ -803,13 +1076,17 @@ int pdeode_set_initial_condition(pdeode_ctx *c, int ic, double depth, double hei
     int rc = zero_array(c, 1);                       // Mnew := 0, the first warm start (D8)
     if (rc) return rc;
     c->warm = false;
-    c->mass_valid = false;
+    c->mass_valid = false; c->sums_valid = false;
     CK(cudaStreamSynchronize(c->stream));
     return PDEODE_OK;
 }
 
 int pdeode_get_state(pdeode_ctx *c, double *M, double *C) {
     if (!c || !M || !C) return PDEODE_ERR_ARG;
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) {
+        const size_t off = (size_t)m->g.row0 * (size_t)m->g.col;
+        return pdeode_get_state(m, M + off, C + off);
+    }));
     CK(cudaSetDevice(c->device));
     int rc;
     if ((rc = download(c, M, c->Mb[c->iM]))) return rc;
@@ -839,6 +1116,14 @@ int frame_buffer(pdeode_ctx *c, size_t doubles) {
 
 int pdeode_frame_size(const pdeode_ctx *c, int filter, int *nrows_out, int *ncols_out) {
     if (!c || filter < 1) return PDEODE_ERR_ARG;
+    if (c->group) {
+        std::vector<int> nro; int nco = 0, tot = 0;
+        group_frame_rows(const_cast<pdeode_ctx *>(c), filter, nro, &nco);
+        for (int v : nro) tot += v;
+        if (nrows_out) *nrows_out = tot;
+        if (ncols_out) *ncols_out = nco;
+        return PDEODE_OK;
+    }
     int first, nro, nco;
     frame_rows(c, filter, &first, &nro, &nco);
     if (nrows_out) *nrows_out = nro;
@@ -848,6 +1133,15 @@ int pdeode_frame_size(const pdeode_ctx *c, int filter, int *nrows_out, int *ncol
 
 int pdeode_get_frame(pdeode_ctx *c, int filter, double *M, double *C) {
     if (!c || !M || !C || filter < 1) return PDEODE_ERR_ARG;
+    if (c->group) {
+        std::vector<int> nro; int nco = 0;
+        group_frame_rows(c, filter, nro, &nco);
+        std::vector<size_t> off(nro.size(), 0);
+        for (size_t k = 1; k < nro.size(); ++k) off[k] = off[k - 1] + (size_t)nro[k - 1] * (size_t)nco;
+        return group_run(c, [&](int k, pdeode_ctx *m) {
+            return pdeode_get_frame(m, filter, M + off[(size_t)k], C + off[(size_t)k]);
+        });
+    }
     CK(cudaSetDevice(c->device));
     int first, nro, nco;
     frame_rows(c, filter, &first, &nro, &nco);
@@ -866,6 +1160,15 @@ int pdeode_get_frame(pdeode_ctx *c, int filter, double *M, double *C) {
 
 int pdeode_get_frame_rowmeans(pdeode_ctx *c, int filter, double *meanM, double *meanC) {
     if (!c || !meanM || !meanC || filter < 1) return PDEODE_ERR_ARG;
+    if (c->group) {
+        std::vector<int> nro; int nco = 0;
+        group_frame_rows(c, filter, nro, &nco);
+        std::vector<size_t> off(nro.size(), 0);
+        for (size_t k = 1; k < nro.size(); ++k) off[k] = off[k - 1] + (size_t)nro[k - 1];
+        return group_run(c, [&](int k, pdeode_ctx *m) {
+            return pdeode_get_frame_rowmeans(m, filter, meanM + off[(size_t)k], meanC + off[(size_t)k]);
+        });
+    }
     CK(cudaSetDevice(c->device));
     int first, nro, nco;
     frame_rows(c, filter, &first, &nro, &nco);
@@ -940,6 +1243,8 @@ int step_whole(pdeode_ctx *c, int nsteps) {
     c->ip = o.ip; c->p = c->pbuf[c->ip];
     c->warm = c->warm || o.count > 0 || o.steps_done > 0;
     c->mass_valid = false;
+    c->sums_valid = o.have_sums != 0;
+    c->sumM = o.sumM; c->sumC = o.sumC;
     c->trace_count = std::min(o.count, std::min(MAX_PICARD_TRACE, STEP_TRACE));
     for (int k = 0; k < c->trace_count; ++k) {
         c->nit_trace[k] = o.nit[k];
@@ -960,6 +1265,18 @@ inline bool whole_step_path(const pdeode_ctx *c) {
 // P:700-742
 int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *nitMax) {
     if (!c) return PDEODE_ERR_ARG;
+    if (c->group) {
+        // every slab takes the same decisions (same all-rank sums): member 0's counts are the step's
+        const int n = c->group->n;
+        std::vector<int> cnt((size_t)n, 0); std::vector<long long> ns((size_t)n, 0), nm((size_t)n, 0);
+        const int rc = group_run(c, [&](int k, pdeode_ctx *m) {
+            return pdeode_step(m, &cnt[(size_t)k], &ns[(size_t)k], &nm[(size_t)k]);
+        });
+        if (countIters) *countIters = cnt[0];
+        if (nitSum) *nitSum = ns[0];
+        if (nitMax) *nitMax = nm[0];
+        return rc;
+    }
     CK(cudaSetDevice(c->device));
     if (whole_step_path(c)) {                        // the whole step in one launch
         const int rc1 = step_whole(c, 1);
@@ -991,10 +1308,6 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         if (!c->warm) inew = c->iMnew;               // the zeroed buffer (first solve ever)
         const double *x0 = c->warm ? c->Mb[c->iM] : c->Mb[inew];
         long long nit = 0; int stop = 0;
-        if ((rc = solve(c, x0, c->Mb[inew], count, &nit, &stop))) return rc;
-        c->warm = true;
-        c->iMnew = inew;
-
         int icnew = 0;
         while (icnew == c->iCprev || icnew == c->iC) icnew++;
         SolveCArgs s{};
@@ -1003,20 +1316,27 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         s.Ccur = c->Cb[c->iC]; s.Mcur = c->Mb[c->iM]; s.Cnew = c->Cb[icnew];
         s.n2 = (long long)c->g.rows * c->g.P / 2;
         s.fuse_scalars = (multi(c) || c->serial) ? 0 : 1;
-        s.seq = c->seq;
-        CK(launch_solvec(s, c->stream));             // P:717, P:725-726
-        c->launches++;
-        if (c->serial) {                             // calcDiff x2 in cell order (P:956-960)
-            const SerialJob jb[2] = {{s.Ccur, s.Cnew, SER_ABSDIFF, 0}, {s.Mcur, s.Mnew, SER_ABSDIFF, 0}};
-            if ((rc = serial_sums(c, jb, 2, c->S->part))) return rc;
-        }
-        if (multi(c) || c->serial) {
-            if (multi(c) && (rc = allreduce_part(c, 2))) return rc;
-            CK(launch_scal_after_solvec(c->S, c->g, c->stream));
+        bool solvec_done = false;
+        if ((rc = solve(c, x0, c->Mb[inew], count, &nit, &stop, &s, &solvec_done))) return rc;
+        c->warm = true;
+        c->iMnew = inew;
+
+        if (!solvec_done) {
+            s.seq = c->seq; s.gated = 0;
+            CK(launch_solvec(s, c->stream));             // P:717, P:725-726
             c->launches++;
+            if (c->serial) {                             // calcDiff x2 in cell order (P:956-960)
+                const SerialJob jb[2] = {{s.Ccur, s.Cnew, SER_ABSDIFF, 0}, {s.Mcur, s.Mnew, SER_ABSDIFF, 0}};
+                if ((rc = serial_sums(c, jb, 2, c->S->part))) return rc;
+            }
+            if (multi(c) || c->serial) {
+                if (multi(c) && (rc = allreduce_part(c, 4))) return rc;
+                CK(launch_scal_after_solvec(c->S, c->g, c->stream));
+                c->launches++;
+            }
+            if ((rc = snapshot(c, 0))) return rc;
+            if ((rc = wait_snapshot(c, 0))) return rc;
         }
-        if ((rc = snapshot(c, 0))) return rc;
-        if ((rc = wait_snapshot(c, 0))) return rc;
         diffC = c->snap[0].s.diffC;
         diffM = c->snap[0].s.diffM;
         if (c->pending_persist) {
@@ -1051,6 +1371,10 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         }
         count++;                                     // P:730
         c->mass_valid = false;
+        // calcMass of the new iterate came with the C update (not in serial-order verification,
+        // where pdeode_mass adds in cell order itself)
+        c->sums_valid = !c->serial;
+        c->sumM = c->snap[0].s.sumM; c->sumC = c->snap[0].s.sumC;
         if (count > PICARD_CAP) {                    // P:732
             if (countIters) *countIters = count;
             if (nitSum) *nitSum = sum;
@@ -1068,6 +1392,20 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
 int pdeode_step_many(pdeode_ctx *c, int n, int *stepsDone, long long *countSum, int *countMax,
                      long long *nitSum, long long *nitMax) {
     if (!c || n < 0) return PDEODE_ERR_ARG;
+    if (c->group) {
+        const int ng = c->group->n;
+        std::vector<int> sd((size_t)ng, 0), cm((size_t)ng, 0);
+        std::vector<long long> cs((size_t)ng, 0), ns((size_t)ng, 0), nm((size_t)ng, 0);
+        const int rc = group_run(c, [&](int k, pdeode_ctx *m) {
+            return pdeode_step_many(m, n, &sd[(size_t)k], &cs[(size_t)k], &cm[(size_t)k], &ns[(size_t)k], &nm[(size_t)k]);
+        });
+        if (stepsDone) *stepsDone = sd[0];
+        if (countSum) *countSum = cs[0];
+        if (countMax) *countMax = cm[0];
+        if (nitSum) *nitSum = ns[0];
+        if (nitMax) *nitMax = nm[0];
+        return rc;
+    }
     CK(cudaSetDevice(c->device));
     int done = 0, cmax = 0, warn = 0, rc = PDEODE_OK;
     long long csum = 0, nsum = 0, nmax = 0;
@@ -1109,7 +1447,21 @@ int pdeode_step_many(pdeode_ctx *c, int n, int *stepsDone, long long *countSum, 
 
 int pdeode_mass(pdeode_ctx *c, double *meanM, double *meanC) {
     if (!c) return PDEODE_ERR_ARG;
+    if (c->group) {
+        const int n = c->group->n;
+        std::vector<double> a((size_t)n, 0.0), b((size_t)n, 0.0);
+        const int rc = group_run(c, [&](int k, pdeode_ctx *m) { return pdeode_mass(m, &a[(size_t)k], &b[(size_t)k]); });
+        if (meanM) *meanM = a[0];
+        if (meanC) *meanC = b[0];
+        return rc;
+    }
     CK(cudaSetDevice(c->device));
+    if (c->sums_valid && !c->mass_valid) {
+        // the sums came with the last C update of the step (k_solvec / the whole-step launch)
+        if (meanM) *meanM = c->sumM / c->g.n_glob;           // P:789
+        if (meanC) *meanC = c->sumC / c->g.n_glob;
+        return PDEODE_OK;
+    }
     int rc = run_mass(c);
     if (rc) return rc;
     if (meanM) *meanM = c->snap[0].s.sumM / c->g.n_glob;     // P:789
@@ -1119,6 +1471,19 @@ int pdeode_mass(pdeode_ctx *c, double *meanM, double *meanC) {
 
 int pdeode_peak(pdeode_ctx *c, double *peak, double *height, double *intfac) {
     if (!c) return PDEODE_ERR_ARG;
+    if (c->group) {
+        // outputs the reference would leave unassigned stay untouched: start every member from the caller's values
+        const int n = c->group->n;
+        std::vector<double> pk((size_t)n, peak ? *peak : 0.0), he((size_t)n, height ? *height : 0.0),
+            it((size_t)n, intfac ? *intfac : 0.0);
+        const int rc = group_run(c, [&](int k, pdeode_ctx *m) {
+            return pdeode_peak(m, &pk[(size_t)k], &he[(size_t)k], &it[(size_t)k]);
+        });
+        if (peak) *peak = pk[0];
+        if (height) *height = he[0];
+        if (intfac) *intfac = it[0];
+        return rc;
+    }
     CK(cudaSetDevice(c->device));
     int rc = run_mass(c);
     if (rc) return rc;
@@ -1136,6 +1501,7 @@ int pdeode_peak(pdeode_ctx *c, double *peak, double *height, double *intfac) {
 
 int pdeode_set_maxit(pdeode_ctx *c, long long maxit) {
     if (!c) return PDEODE_ERR_ARG;
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) { return pdeode_set_maxit(m, maxit); }));
     CK(cudaSetDevice(c->device));
     c->maxit = maxit >= 0 ? maxit : c->maxit_default;
     CK(cudaStreamSynchronize(c->stream));
@@ -1146,6 +1512,7 @@ int pdeode_set_maxit(pdeode_ctx *c, long long maxit) {
 int pdeode_last_step_trace(pdeode_ctx *c, long long *nit_per_solve, double *diffs, int cap,
                            int *count) {
     if (!c) return PDEODE_ERR_ARG;
+    GROUP(c, pdeode_last_step_trace(c->group->m[0], nit_per_solve, diffs, cap, count));
     const int k = std::min(cap, c->trace_count);
     for (int i = 0; i < k; ++i) {
         if (nit_per_solve) nit_per_solve[i] = c->nit_trace[i];
@@ -1157,6 +1524,7 @@ int pdeode_last_step_trace(pdeode_ctx *c, long long *nit_per_solve, double *diff
 
 int pdeode_cg_trace_enable(pdeode_ctx *c, int cap) {
     if (!c || cap < 0) return PDEODE_ERR_ARG;
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) { return pdeode_cg_trace_enable(m, cap); }));
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     if (c->trace) { cudaFree(c->trace); c->trace = nullptr; }
@@ -1168,6 +1536,7 @@ int pdeode_cg_trace_enable(pdeode_ctx *c, int cap) {
 
 int pdeode_cg_trace_get(pdeode_ctx *c, double *out, int cap, int *count) {
     if (!c || !out) return PDEODE_ERR_ARG;
+    GROUP(c, pdeode_cg_trace_get(c->group->m[0], out, cap, count));
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
     int len = 0;
@@ -1180,6 +1549,9 @@ int pdeode_cg_trace_get(pdeode_ctx *c, double *out, int cap, int *count) {
 
 int pdeode_debug_get_array(pdeode_ctx *c, int which, double *out) {
     if (!c || !out) return PDEODE_ERR_ARG;
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) {
+        return pdeode_debug_get_array(m, which, out + (size_t)m->g.row0 * (size_t)m->g.col);
+    }));
     CK(cudaSetDevice(c->device));
     const double *src = nullptr;
     switch (which) {
@@ -1201,12 +1573,19 @@ int pdeode_debug_get_array(pdeode_ctx *c, int which, double *out) {
 
 int pdeode_exchange_mode(const pdeode_ctx *c, int *mode) {
     if (!c || !mode) return PDEODE_ERR_ARG;
+    GROUP(c, pdeode_exchange_mode(c->group->m[0], mode));
     *mode = !multi(c) ? 0 : (c->peer ? 2 : 1);
     return PDEODE_OK;
 }
 
 int pdeode_engine_info(const pdeode_ctx *c, char *buf, int len) {
     if (!c || !buf || len < 1) return PDEODE_ERR_ARG;
+    if (c->group) {
+        char one[512];
+        const int rc = pdeode_engine_info(c->group->m[0], one, (int)sizeof one);
+        snprintf(buf, (size_t)len, "%s gpus=%d(one process)", one, c->group->n);
+        return rc;
+    }
     snprintf(buf, (size_t)len,
              "spmv=%s BS=%d TR=%d depth=%d init_BS=%d init_TR=%d persist=%d persist_ctas=%d "
              "defer_x=%d kb_reverse=%d whole_step=%d step_BS=%d step_ctas=%d exchange=%s sum_order=%s",
@@ -1222,6 +1601,12 @@ int pdeode_engine_info(const pdeode_ctx *c, char *buf, int len) {
 
 int pdeode_launch_count(const pdeode_ctx *c, long long *launches) {
     if (!c || !launches) return PDEODE_ERR_ARG;
+    if (c->group) {
+        long long tot = 0;
+        for (pdeode_ctx *m : c->group->m) tot += m ? m->launches : 0;
+        *launches = tot;
+        return PDEODE_OK;
+    }
     *launches = c->launches;
     return PDEODE_OK;
 }
@@ -1241,6 +1626,7 @@ int pdeode_kernel_bytes_per_cell(int kernel) {
 
 int pdeode_time_kernel(pdeode_ctx *c, int kernel, int reps, float *ms_per_launch) {
     if (!c || reps < 1 || !ms_per_launch) return PDEODE_ERR_ARG;
+    if (c->group) return PDEODE_ERR_ARG;
     if (multi(c)) return PDEODE_ERR_ARG;
     CK(cudaSetDevice(c->device));
     CK(cudaStreamSynchronize(c->stream));
@@ -1298,7 +1684,7 @@ int pdeode_time_kernel(pdeode_ctx *c, int kernel, int reps, float *ms_per_launch
     *ms_per_launch = ms / (float)reps;
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
-    c->mass_valid = false;
+    c->mass_valid = false; c->sums_valid = false;
     return PDEODE_OK;
 }
 

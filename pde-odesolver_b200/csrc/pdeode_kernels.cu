@@ -131,6 +131,41 @@ __device__ __forceinline__ bool grid_sum2(double &a, double &b, double *partials
     return threadIdx.x == 0;
 }
 
+// The same for NV values (partials: [NV][nb]); sm: 64 doubles.
+template <int NV>
+__device__ __forceinline__ bool grid_sum(double (&v)[NV], double *partials, int nb, int bid,
+                                         unsigned int *ticket, double *sm) {
+    __shared__ int s_lastN;
+    double z = 0.0;
+#pragma unroll
+    for (int k = 0; k + 1 < NV; k += 2) block_sum2(v[k], v[k + 1], sm);
+    if (NV & 1) block_sum2(v[NV - 1], z, sm);
+    if (threadIdx.x == 0) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) partials[k * nb + bid] = v[k];
+        __threadfence();
+        const unsigned int t = atomicAdd(ticket, 1u);
+        s_lastN = (t == (unsigned int)(nb - 1));
+    }
+    __syncthreads();
+    if (!s_lastN) return false;
+    __threadfence();
+    double x[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k) x[k] = 0.0;
+    for (int i = threadIdx.x; i < nb; i += blockDim.x) {
+#pragma unroll
+        for (int k = 0; k < NV; ++k) x[k] += __ldcg(partials + k * nb + i);
+    }
+#pragma unroll
+    for (int k = 0; k + 1 < NV; k += 2) block_sum2(x[k], x[k + 1], sm);
+    if (NV & 1) block_sum2(x[NV - 1], z, sm);
+#pragma unroll
+    for (int k = 0; k < NV; ++k) v[k] = x[k];
+    if (threadIdx.x == 0) *ticket = 0u;
+    return threadIdx.x == 0;
+}
+
 // Same for a triple (partials: [3][nb]).
 __device__ __forceinline__ bool grid_sum3(double &a, double &b, double &c, double *partials,
                                           int nb, int bid, unsigned int *ticket, double *sm,
@@ -172,7 +207,7 @@ __device__ __forceinline__ void scal_after_init(DevScal *S, double rr, double xx
     S->rho = rr;          // dotProd(r,r) seen by iteration 1 (CG:59)
     S->rho_old = 0.0;     // CG:44
     S->xx = xx;           // sum(sol*sol) seen by iteration 1 (CG:57)
-    S->nit = 0; S->stop = 0; S->done = 0; S->finished = 0;
+    S->nit = 0; S->stop = 0; S->done = 0; S->finished = 0; S->tail = 0;
     S->trace_len = 0;
 }
 
@@ -208,6 +243,11 @@ __device__ __forceinline__ void scal_after_solvec(DevScal *S, double dC, double 
     S->diffC = dC / n_glob;
     S->diffM = dM / n_glob;
 }
+// sums of the new iterate, for calcMass (P:783-787) without another pass over the fields
+__device__ __forceinline__ void scal_mass_sums(DevScal *S, double sM, double sC) {
+    S->sumM = sM;
+    S->sumC = sC;
+}
 
 __global__ void k_scal_after_init(DevScal *S) { scal_after_init(S, S->part[0], S->part[1]); }
 __global__ void k_scal_after_spmv(DevScal *S, GridDesc g, double tol2, double *trace) {
@@ -220,6 +260,7 @@ __global__ void k_scal_after_update(DevScal *S) {
 }
 __global__ void k_scal_after_solvec(DevScal *S, GridDesc g) {
     scal_after_solvec(S, S->part[0], S->part[1], g.n_glob);
+    scal_mass_sums(S, S->part[2], S->part[3]);
 }
 
 // ---------------------------------------------------------------- serial-order sums (verification)
@@ -1105,6 +1146,12 @@ __global__ void __launch_bounds__(256) k_update(const UpdateArgs a) {
     __shared__ double sm[64];
     DevScal *S = a.S;
     if (S->finished) return;
+    if (a.tail_ok && S->done) {
+        // the last iteration (CG:88-90 said stop): r -= alfa q is dead, the two sums are dead,
+        // and sol += alfa p is applied by k_solvec, which reads sol anyway
+        if (blockIdx.x == 0 && threadIdx.x == 0) { S->tail = 1; S->finished = 1; }
+        return;
+    }
     const bool peer = (a.fuse_scalars == SUMS_PEER);
     const bool r_only = a.r_only != 0;          // 88-byte iteration: x belongs to the SpMV kernel
     double alfa, pq_glob = 0.0, pp_glob = 0.0, xx_post = 0.0;
@@ -1186,6 +1233,10 @@ __global__ void __launch_bounds__(256) k_update_r(const UpdateArgs a) {
     __shared__ double sm[64];
     DevScal *S = a.S;
     if (S->finished) return;
+    if (a.tail_ok && S->done) {                 // see k_update
+        if (blockIdx.x == 0 && threadIdx.x == 0) { S->tail = 1; S->finished = 1; }
+        return;
+    }
     const double alfa = S->alfa;
     const bool rev = a.reverse != 0;
     double rr = 0.0, zz = 0.0;
@@ -1535,31 +1586,51 @@ __device__ __forceinline__ double solve_c_cell(double Mp, double Mn, double Cp,
     return 0.5 * (-b + sqrt(b * b - 4.0 * c));
 }
 
+// C update (P:504-506), the two Picard residuals (P:948-963) and the field sums of the new
+// iterate (calcMass, P:783-787) in one pass.  With DevScal::tail pending it also applies the
+// last CG iteration's sol += alfa p (CG:80) on the way -- the update kernel of that iteration
+// did nothing -- so that the final iteration of a solve and the C update cost 64 B per cell
+// instead of 96.
 __global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
     __shared__ double sm[64];
+    DevScal *S = a.S;
+    if (a.gated && (!S->finished || S->solvec_seq == a.seq)) return;
     const GridDesc g = a.g;
     const NumParams np = a.np;
-    double dC = 0.0, dM = 0.0;
+    const bool tail = S->tail != 0;
+    const double alfa = S->alfa;
+    const double *p_last = a.pbuf[(a.ip0 ^ (int)(S->nit & 1)) & 1];
+    double v[4] = {0.0, 0.0, 0.0, 0.0};       // dC, dM, sum Mnew, sum Cnew
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n2; i += stride) {
         const long long k = 2 * i;
         const int j = (int)(k % g.P);
         const bool v0 = j < g.col, v1 = j + 1 < g.col;
-        const double2 mp = ld2(a.Mprev + k), mn = ld2(a.Mnew + k), cp = ld2(a.Cprev + k);
+        const double2 mp = ld2(a.Mprev + k), cp = ld2(a.Cprev + k);
         const double2 cc = ld2(a.Ccur + k), mc = ld2(a.Mcur + k);
+        double2 mn = ld2(a.Mnew + k);
+        if (tail) {
+            const double2 p2 = ld2(p_last + k);
+            mn.x = mn.x + alfa * p2.x; mn.y = mn.y + alfa * p2.y;     // CG:80 of the last iteration
+            st2(a.Mnew + k, mn);
+        }
         double2 cn;
         cn.x = v0 ? solve_c_cell(mp.x, mn.x, cp.x, np) : 0.0;
         cn.y = v1 ? solve_c_cell(mp.y, mn.y, cp.y, np) : 0.0;
         if (np.gSelect == 1) st2(a.Cnew + k, cn);        // P:501
         else cn = ld2(a.Cnew + k);                        // Cnew left as it was
-        dC += v0 ? fabs(cc.x - cn.x) : 0.0;               // P:958
-        dC += v1 ? fabs(cc.y - cn.y) : 0.0;
-        dM += v0 ? fabs(mc.x - mn.x) : 0.0;
-        dM += v1 ? fabs(mc.y - mn.y) : 0.0;
+        v[0] += v0 ? fabs(cc.x - cn.x) : 0.0;             // P:958
+        v[0] += v1 ? fabs(cc.y - cn.y) : 0.0;
+        v[1] += v0 ? fabs(mc.x - mn.x) : 0.0;
+        v[1] += v1 ? fabs(mc.y - mn.y) : 0.0;
+        v[2] += v0 ? mn.x : 0.0; v[2] += v1 ? mn.y : 0.0; // P:785
+        v[3] += v0 ? cn.x : 0.0; v[3] += v1 ? cn.y : 0.0;
     }
-    if (grid_sum2(dC, dM, a.partials, gridDim.x, blockIdx.x, &a.S->ticket[TICKET_SOLVEC], sm)) {
-        if (a.fuse_scalars) scal_after_solvec(a.S, dC, dM, g.n_glob);
-        else { a.S->part[0] = dC; a.S->part[1] = dM; }
+    if (grid_sum<4>(v, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_SOLVEC], sm)) {
+        if (a.fuse_scalars) { scal_after_solvec(S, v[0], v[1], g.n_glob); scal_mass_sums(S, v[2], v[3]); }
+        else { S->part[0] = v[0]; S->part[1] = v[1]; S->part[2] = v[2]; S->part[3] = v[3]; }
+        S->tail = 0;
+        S->solvec_seq = a.seq;
     }
 }
 
@@ -1946,8 +2017,25 @@ __global__ void __launch_bounds__(512) k_step_persist(const StepArgs A) {
     nit_sum += nsum;
     if (nmax > nit_max) nit_max = nmax;
     }   // time steps
+    // calcMass of the state the launch leaves (P:783-787): the diagnostics that follow a stretch
+    // of steps (P:665-669) then need no pass and no launch of their own
+    double msum[2] = {0.0, 0.0};
+    bool have_sums = false;
+    if (!SERIAL && ok) {
+        if (inrow) {
+            const double *Mf = A.Mb[iM], *Cf = A.Cb[iC];
+            long long off = off0;
+            for (int i = i_begin; i < i_end; ++i, off += g.P) {
+                const double2 m = ld2(Mf + off), c2 = ld2(Cf + off);
+                msum[0] += v0 ? m.x : 0.0; msum[0] += v1 ? m.y : 0.0;     // P:785
+                msum[1] += v0 ? c2.x : 0.0; msum[1] += v1 ? c2.y : 0.0;
+            }
+        }
+        have_sums = step_allsum<2>(msum, A.slots, A.counter, err, ++gen, G, sm, s_tot);
+    }
     if (blockIdx.x == 0 && tid == 0) {
         StepOut *o = A.out;
+        o->sumM = msum[0]; o->sumC = msum[1]; o->have_sums = have_sums ? 1 : 0;
         o->steps_done = steps_done; o->count_sum = count_sum; o->count_max = count_max;
         o->nit_sum_all = nit_sum; o->nit_max_all = nit_max;
         o->nit_sum = nsum; o->nit_max = nmax; o->count = count;

@@ -70,6 +70,7 @@ def _lib():
         "pdeode_create": [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Params), C.c_int],
         "pdeode_create_dist": [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Params), C.c_int,
                                C.c_int, C.c_int, vp],
+        "pdeode_create_group": [C.POINTER(vp), C.c_int, C.c_int, C.POINTER(Params), C.c_int, ip],
         "pdeode_nccl_unique_id": [vp],
         "pdeode_destroy": [vp],
         "pdeode_local_rows": [vp, ip, ip],
@@ -133,12 +134,19 @@ def _ptr(a):
 class Solver:
     """Device-resident stepper: the loop body of solveOrder2 (P:700-742)."""
 
-    def __init__(self, row, col, params, device=0, rank=0, nranks=1, nccl_id=None):
+    def __init__(self, row, col, params, device=0, rank=0, nranks=1, nccl_id=None, ngpus=1,
+                 devices=None):
+        """ngpus > 1: row slabs over several GPUs of THIS process (pdeode_create_group); the
+        object then behaves like a single-GPU solver of the whole grid.  nranks > 1: one slab
+        of a multi-process solve (pdeode_create_dist)."""
         self.lib = _lib()
         self.row, self.col = row, col
         self.params = params
         self.h = C.c_void_p()
-        if nranks == 1:
+        if ngpus > 1:
+            devs = (C.c_int * ngpus)(*(devices if devices is not None else range(ngpus)))
+            rc = self.lib.pdeode_create_group(C.byref(self.h), row, col, C.byref(params), ngpus, devs)
+        elif nranks == 1:
             rc = self.lib.pdeode_create(C.byref(self.h), row, col, C.byref(params), device)
         else:
             idbuf = C.create_string_buffer(nccl_id, NCCL_ID_BYTES)

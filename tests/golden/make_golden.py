@@ -41,43 +41,7 @@ def initial(kind, row, col):
     raise ValueError(kind)
 
 
-NEAR = 1.25      # a CG iteration whose err2 came within this factor of the stop threshold
-NEAR_CAP = 32
-
-
-class _Trace(C.Structure):
-    _fields_ = [(k, C.c_double) for k in ("rho", "dot", "alfa", "err2", "normx")]
-
-
-def replay_step(lib, p, row, col, M, Cc, Mnew):
-    """One time step (P:700-742) from the oracle's building blocks, with the CG
-    trace of every solve.  Returns (nits, near): near[s] lists the iterations of
-    solve s where the reference came within NEAR of stopping (CG:90) but did
-    not -- where a different summation order may well stop."""
-    n = row * col
-    Mprev, Cprev = M.copy(), Cc.copy()
-    M, Cc, Mnew = M.copy(), Cc.copy(), Mnew.copy()
-    diffC = diffM = 1.0
-    nits, near = [], []
-    cap = 4096
-    while diffC + diffM > p.eSoln:
-        A = np.zeros(5 * n); rhs = np.zeros(n); ioff = np.zeros(5, np.int32)
-        lib.oracle_gen_matrix(Mprev, Cc, A, ioff, rhs, row, col, C.byref(p))
-        nit = C.c_longlong(100 * n); e1 = C.c_double(p.e1); e2 = C.c_double(p.e2)
-        st = C.c_int(); scr = np.zeros(3 * n); tr = (_Trace * cap)()
-        lib.oracle_solve_ls_diag(n, 5, ioff, A, Mnew, rhs, C.byref(nit), C.byref(e1), C.byref(e2),
-                                 C.byref(st), scr, C.cast(tr, C.c_void_p), cap)
-        k = int(nit.value)
-        nits.append(k)
-        hits = [i + 1 for i in range(min(k, cap) - 1) if tr[i].err2 < NEAR * p.e2 * tr[i].normx]
-        near.append(hits if len(hits) <= NEAR_CAP else hits[:NEAR_CAP // 2] + hits[-NEAR_CAP // 2:])
-        Cn = np.empty(n)
-        lib.oracle_solve_c(Mprev, Mnew, Cprev, Cn, n, p.kappa, p.gama, p.tDel, p.gSelect)
-        diffC = lib.oracle_calc_diff(Cc, Cn, row, col)
-        diffM = lib.oracle_calc_diff(M, Mnew, row, col)
-        Cc = Cn
-        M = Mnew.copy()
-    return nits, near
+NEAR, NEAR_CAP, replay_step = ol.NEAR, ol.NEAR_CAP, ol.replay_step
 
 
 def run(name):

@@ -113,40 +113,48 @@ def test_odd_shapes_bit_identical(pb, engine_env, engine, row, col):
 @pytest.mark.parametrize("name", [n for n in REF_CASES if n != "beta6_25"])
 @pytest.mark.parametrize("engine", ["kernels", "kernels-96", "persistent", "whole-step"])
 def test_default_order_against_reference_vectors(pb, engine_env, engine, name):
-    """Production summation order against the reference's vectors.  Picard counts: exact.
-    CG iterations per step: within +-2 per solve (BASELINE north_star) -- or, where the
-    reference's own serial and OpenMP builds (same algorithm, other summation order; the oracle
-    built both ways, the serial one being bit-identical to these vectors) are further apart than
-    that, within twice THEIR distance.  Fields: 1e-9 relative L2 while every step took the
-    reference's iteration count and the reference's two builds agree to 1e-10, one CG step
-    (20 e2) otherwise.  (beta6_25 is left to the serial-order test: its solves stagnate to the
-    100 n cap, where the iteration count is decided by rounding.)"""
+    """Production summation order against the reference's vectors.
+      * Picard counts: exact, always.
+      * CG iterations per solve: the reference's count +-2 (BASELINE north_star), or +-2 around an
+        iteration where the reference's own err2 came within 25 % of the stop threshold (CG:90)
+        without crossing it -- a solve on such a plateau stops there under any other summation
+        order.  Asserted while the run is in lockstep with the reference, i.e. up to and
+        including the first step in which a count differs: after that the two runs are different
+        realisations of the same tolerance (the next solve starts 1e-8 away) and per-solve counts
+        stop being comparable -- as between the reference's own serial and OpenMP builds.
+      * Fields: 1e-9 relative L2 while in lockstep (and the reference's two builds agree to
+        1e-10), one CG step (20 e2) afterwards, at every recorded step.
+    (beta6_25 is left to the serial-order test: its solves stagnate to the 100 n cap.)"""
     engine_env(engine)
     z, row, col, p = load_ref_case(name)
     s = pb.Solver(row, col, gpu_params(pb, p))
     o1 = ol.Oracle(row, col, p)
     o2 = ol.Oracle(row, col, p, omp=True)
+    lib = ol.load()
     for x in (s, o1, o2):
         x.set_state(z["M0"], z["C0"])
     done = 0
-    env_cnt = 0
-    same = True
+    lockstep = True
     for k, nst in enumerate(int(v) for v in z["nsteps"]):
         while done < nst:
-            g = s.step(); r1 = o1.step(); r2 = o2.step()
-            assert g["countIters"] == r1["countIters"], (engine, name, done)      # Picard: exact
-            env_cnt = max(env_cnt, abs(r2["nitSum"] - r1["nitSum"]))
-            tol_cg = max(2 * r1["countIters"], 2 * env_cnt)
-            assert abs(g["nitSum"] - r1["nitSum"]) <= tol_cg, (engine, name, done, g, r1, env_cnt)
-            same = same and g["nitSum"] == r1["nitSum"]
+            if lockstep:
+                Mk, Ck = o1.get_state()
+                _, near = ol.replay_step(lib, p, row, col, Mk, Ck, o1.get_mnew())
+            g = s.step_trace(); r1 = o1.step(); o2.step()
+            assert g["countIters"] == r1["countIters"], (engine, name, done, g, r1)   # Picard: exact
+            if lockstep:
+                for si, (a, b) in enumerate(zip(g["nits"], r1["nits"])):
+                    cands = [b] + (near[si] if si < len(near) else [])
+                    assert min(abs(a - c) for c in cands) <= 2, (engine, name, done, si, g["nits"], r1["nits"], cands)
+                lockstep = g["nits"] == r1["nits"]
             done += 1
         Mo, Co = o1.get_state()
         assert np.array_equal(Mo, z["M"][k]) and np.array_equal(Co, z["C"][k])    # oracle == reference
         M2, C2 = o2.get_state()
         env = max(np.linalg.norm(M2 - Mo) / np.linalg.norm(Mo), np.linalg.norm(C2 - Co) / np.linalg.norm(Co))
-        tol = 1e-9 if (same and env <= 1e-10) else max(1e-9, 20 * p.e2)
+        tol = 1e-9 if (lockstep and env <= 1e-10) else max(1e-9, 20 * p.e2)
         M, C = s.get_state()
         eM = np.linalg.norm(M - z["M"][k]) / np.linalg.norm(z["M"][k])
         eC = np.linalg.norm(C - z["C"][k]) / np.linalg.norm(z["C"][k])
-        assert eM <= tol and eC <= tol, (engine, name, nst, eM, eC, tol, env)
+        assert eM <= tol and eC <= tol, (engine, name, nst, eM, eC, tol, env, lockstep)
     s.close(); o1.close(); o2.close()
