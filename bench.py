@@ -244,6 +244,54 @@ def run_reference(args):
     emit(out)
 
 
+def run_ensemble(args):
+    """BASELINE config 5: `--ensemble` independent solves (the reference's sweep was numbered
+    parameter files, .gitignore:34-35; one <name>Output/ each as runAll.sh:13-20) dealt over
+    the first --gpus GPUs by pde-odesolver_b200/bin/pdeode_ensemble -- replicas, no
+    communication.  Wall clock around the whole program: contexts, files and output included."""
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    import ensemble_bench as eb
+    exe = os.path.join(ROOT, "pde-odesolver_b200", "bin", "pdeode_ensemble")
+    grid, steps, members = args.ensemble_grid, args.ensemble_steps, args.ensemble
+    n = grid * grid
+    with tempfile.TemporaryDirectory() as d:
+        files = []
+        for k in range(1, members + 1):
+            with open(os.path.join(d, f"{k}.txt"), "w") as fh:
+                fh.write(eb.TEMPLATE.format(**eb.member_params(k, grid, steps)))
+            files.append(f"{k}.txt")
+        env = dict(os.environ, PDEODE_MEMBERS_PER_GPU=str(args.ensemble_per_gpu), PDEODE_SEED="1",
+                   PDEODE_DEVICES=",".join(str(i) for i in range(max(1, args.gpus))))
+        clk = ClockSampler(0)
+        clk.start()
+        t0 = time.perf_counter()
+        r = subprocess.run([exe] + files, cwd=d, env=env, capture_output=True, text=True)
+        dt = time.perf_counter() - t0
+        clocks = clk.stop()
+        if r.returncode != 0:
+            raise SystemExit("bench.py --ensemble: pdeode_ensemble failed: " + (r.stdout + r.stderr)[-800:])
+        cg = 0.0
+        solver_s = []
+        for k in range(1, members + 1):
+            txt = open(os.path.join(d, f"{k}Output", "statReport.dat")).read()
+            cg += eb.stat_value(txt, "Avg Iters for linear") * eb.stat_value(txt, "Avg Iters for iterating") * steps
+            solver_s.append(eb.stat_value(txt, "Time to compute"))
+    emit({
+        "metric": METRIC, "value": n * cg / dt, "unit": UNIT, "n_gpus": max(1, args.gpus),
+        "steps": steps, "warmup": 0, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"ensemble: {members} independent {grid}x{grid} solves of {steps} time steps "
+                               "(numbered parameter files varying delta, nu, kappa, gama, beta, height), "
+                               f"{args.ensemble_per_gpu} members in flight per GPU, replicas only",
+                   "grid": [grid, grid], "members": members, "parallelism": f"replicas over {max(1, args.gpus)} GPUs"},
+        "wall_s": dt, "cg_iterations": round(cg), "clocks": clocks,
+        "member_time_to_compute_s": {"median": float(np.median(solver_s)), "max": float(max(solver_s))},
+        "gpu_launches": None,
+        "note": "wall clock of the whole pdeode_ensemble program, start to exit: context creation, "
+                "console and output files of every member included",
+    })
+
+
 def workload_config(args, nranks):
     return {
         "workload": f"{args.grid}x{args.grid} grid, shipped parameter.txt values, IC MinitialCond=1 "
@@ -297,12 +345,22 @@ def main():
     ap.add_argument("--strong-cg-cap", type=int, default=600,
                     help="CG iterations per step of the stiff 16384^2 sub-record")
     ap.add_argument("--no-parity", action="store_true", help="N > 1: skip the check against one rank")
+    ap.add_argument("--ensemble", type=int, default=0,
+                    help="BASELINE config 5 instead of the headline workload: this many independent "
+                         "512^2 solves (numbered parameter files) spread over --gpus GPUs by "
+                         "pdeode_ensemble, one line with the aggregate throughput")
+    ap.add_argument("--ensemble-grid", type=int, default=512)
+    ap.add_argument("--ensemble-steps", type=int, default=200)
+    ap.add_argument("--ensemble-per-gpu", type=int, default=16)
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                      # timing rule: W >= 3
 
     if args.impl == "reference":
         run_reference(args)
+        return
+    if args.ensemble > 0:
+        run_ensemble(args)
         return
 
     if int(os.environ.get("WORLD_SIZE", "1")) == 1:

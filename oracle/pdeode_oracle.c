@@ -387,6 +387,13 @@ void oracle_get_state(const oracle_state *s, double *M, double *C)
     memcpy(C, s->C, sizeof(double) * (size_t)s->n);
 }
 
+/* Continue a run from a step boundary: there Mnew == M (P:729), which is the warm start of the
+ * next step's first solve (P:714); oracle_set_state alone would start it from zeros. */
+void oracle_set_mnew(oracle_state *s, const double *Mnew)
+{
+    memcpy(s->Mnew, Mnew, sizeof(double) * (size_t)s->n);
+}
+
 void oracle_get_mnew(const oracle_state *s, double *Mnew)
 {
     memcpy(Mnew, s->Mnew, sizeof(double) * (size_t)s->n);

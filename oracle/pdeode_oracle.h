@@ -96,6 +96,7 @@ void oracle_set_state(oracle_state *s, const double *M, const double *C);
 void oracle_get_state(const oracle_state *s, double *M, double *C);
 /* Mnew as left by the last solve (the next warm start). */
 void oracle_get_mnew(const oracle_state *s, double *Mnew);
+void oracle_set_mnew(oracle_state *s, const double *Mnew);
 /* Override the CG iteration cap (default 100*n, P:707).  <0 restores it. */
 void oracle_set_maxit(oracle_state *s, long long maxit);
 

@@ -454,11 +454,25 @@ __device__ __forceinline__ void peer_post(const PeerComm &pc, unsigned long long
 
 // ---------------------------------------------------------------- D(M)
 
+// One IEEE divide and two integer powers per cell: a long dependent chain.  Every thread keeps
+// UNROLL double2 (eight cells at 4) in flight so that the chains overlap; measured 0.111 ms at
+// 4096^2 with one double2 per thread and iteration (fp64 pipe 39 % busy, latency bound).
+template <int UNROLL>
 __global__ void __launch_bounds__(256) k_diffcoef(GridDesc g, NumParams np,
                                                   const double *__restrict__ M,
                                                   double *__restrict__ d, long long n2) {
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2; i += stride) {
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < n2; i += UNROLL * stride) {
+        double2 m[UNROLL], o[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) m[u] = ld2(M + 2 * (i + u * stride));
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) { o[u].x = dfunc(m[u].x, np); o[u].y = dfunc(m[u].y, np); }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) st2(d + 2 * (i + u * stride), o[u]);
+    }
+    for (; i < n2; i += stride) {
         const double2 m = ld2(M + 2 * i);
         double2 o;
         o.x = dfunc(m.x, np);
@@ -1591,6 +1605,7 @@ __device__ __forceinline__ double solve_c_cell(double Mp, double Mn, double Cp,
 // last CG iteration's sol += alfa p (CG:80) on the way -- the update kernel of that iteration
 // did nothing -- so that the final iteration of a solve and the C update cost 64 B per cell
 // instead of 96.
+template <int UNROLL>
 __global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
     __shared__ double sm[64];
     DevScal *S = a.S;
@@ -1602,15 +1617,12 @@ __global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
     const double *p_last = a.pbuf[(a.ip0 ^ (int)(S->nit & 1)) & 1];
     double v[4] = {0.0, 0.0, 0.0, 0.0};       // dC, dM, sum Mnew, sum Cnew
     const long long stride = (long long)gridDim.x * blockDim.x;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < a.n2; i += stride) {
-        const long long k = 2 * i;
+    // two divisions and a square root per cell: UNROLL double2 per thread in flight
+    auto cell_pair = [&](const long long k, const double2 mp, const double2 cp, const double2 cc,
+                         const double2 mc, double2 mn, const double2 p2) {
         const int j = (int)(k % g.P);
         const bool v0 = j < g.col, v1 = j + 1 < g.col;
-        const double2 mp = ld2(a.Mprev + k), cp = ld2(a.Cprev + k);
-        const double2 cc = ld2(a.Ccur + k), mc = ld2(a.Mcur + k);
-        double2 mn = ld2(a.Mnew + k);
         if (tail) {
-            const double2 p2 = ld2(p_last + k);
             mn.x = mn.x + alfa * p2.x; mn.y = mn.y + alfa * p2.y;     // CG:80 of the last iteration
             st2(a.Mnew + k, mn);
         }
@@ -1625,6 +1637,25 @@ __global__ void __launch_bounds__(256) k_solvec(const SolveCArgs a) {
         v[1] += v1 ? fabs(mc.y - mn.y) : 0.0;
         v[2] += v0 ? mn.x : 0.0; v[2] += v1 ? mn.y : 0.0; // P:785
         v[3] += v0 ? cn.x : 0.0; v[3] += v1 ? cn.y : 0.0;
+    };
+    long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    for (; i + (UNROLL - 1) * stride < a.n2; i += UNROLL * stride) {
+        double2 mp[UNROLL], cp[UNROLL], cc[UNROLL], mc[UNROLL], mn[UNROLL], p2[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const long long k = 2 * (i + u * stride);
+            mp[u] = ld2(a.Mprev + k); cp[u] = ld2(a.Cprev + k); cc[u] = ld2(a.Ccur + k);
+            mc[u] = ld2(a.Mcur + k); mn[u] = ld2(a.Mnew + k);
+            p2[u] = tail ? ld2(p_last + k) : make_double2(0.0, 0.0);
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u)
+            cell_pair(2 * (i + u * stride), mp[u], cp[u], cc[u], mc[u], mn[u], p2[u]);
+    }
+    for (; i < a.n2; i += stride) {
+        const long long k = 2 * i;
+        cell_pair(k, ld2(a.Mprev + k), ld2(a.Cprev + k), ld2(a.Ccur + k), ld2(a.Mcur + k),
+                  ld2(a.Mnew + k), tail ? ld2(p_last + k) : make_double2(0.0, 0.0));
     }
     if (grid_sum<4>(v, a.partials, gridDim.x, blockIdx.x, &S->ticket[TICKET_SOLVEC], sm)) {
         if (a.fuse_scalars) { scal_after_solvec(S, v[0], v[1], g.n_glob); scal_mass_sums(S, v[2], v[3]); }
@@ -2443,6 +2474,14 @@ LaunchCfg launch_config(const GridDesc &g) {
     // INIT (sweep at 4096^2): bulk BS 128 x 32 rows 0.200 ms, BS 256 x 64 rows 0.322 ms
     c.i_BS = c.BS > 128 ? 128 : c.BS;
     c.i_TR = c.TR > 32 ? 32 : c.TR;
+    if (const char *e = getenv("PDEODE_INIT_BS")) {
+        const int v = atoi(e);
+        if (v == 64 || v == 128 || v == 256) c.i_BS = v;
+    }
+    if (const char *e = getenv("PDEODE_INIT_TR")) {
+        const int v = atoi(e);
+        if (v >= 1 && v <= 4096) c.i_TR = v;
+    }
     if (const char *e = getenv("PDEODE_KB_REVERSE")) c.kb_reverse = atoi(e) != 0;
 
     // Whole time step in one launch: s_cw threads span a strip (the whole row where P <= 1024),
@@ -2506,7 +2545,10 @@ int stencil_max_blocks(const GridDesc &g, int TR) {
 cudaError_t launch_diffcoef(const GridDesc &g, const NumParams &np, const double *M, double *d,
                             cudaStream_t st) {
     const long long n2 = (long long)g.rows * g.P / 2;
-    k_diffcoef<<<flat_blocks(n2), 256, 0, st>>>(g, np, M, d, n2);
+    static const int unroll = getenv("PDEODE_DIFFCOEF_UNROLL") ? atoi(getenv("PDEODE_DIFFCOEF_UNROLL")) : 4;
+    if (unroll >= 4) k_diffcoef<4><<<flat_blocks((n2 + 3) / 4), 256, 0, st>>>(g, np, M, d, n2);
+    else if (unroll >= 2) k_diffcoef<2><<<flat_blocks((n2 + 1) / 2), 256, 0, st>>>(g, np, M, d, n2);
+    else k_diffcoef<1><<<flat_blocks(n2), 256, 0, st>>>(g, np, M, d, n2);
     return cudaGetLastError();
 }
 
@@ -2520,9 +2562,8 @@ static cudaError_t launch_stencil(const StencilArgs &a, cudaStream_t st) {
     return cudaGetLastError();
 }
 
-template <int BS>
+template <int BS, int DEPTH>
 static cudaError_t launch_init_bulk(const StencilArgs &a, cudaStream_t st) {
-    constexpr int DEPTH = 4;
     constexpr size_t smem = Ring<BS, DEPTH>::BYTES;
     // the attribute is per device: one flag per device, set by whichever thread gets there
     // first (setting it twice is harmless)
@@ -2542,9 +2583,17 @@ static cudaError_t launch_init_bulk(const StencilArgs &a, cudaStream_t st) {
 
 cudaError_t launch_stencil_init(const StencilArgs &a, cudaStream_t st) {
     if (a.variant == 1) {
-        if (a.BS == 64) return launch_init_bulk<64>(a, st);
-        if (a.BS == 128) return launch_init_bulk<128>(a, st);
-        return launch_init_bulk<256>(a, st);
+        // ring depth of the INIT kernel: two IEEE divides per cell make it latency bound, so a
+        // shallower ring (more CTAs per SM) can beat a deeper one (PDEODE_INIT_DEPTH = 2 | 4)
+        static const int depth = getenv("PDEODE_INIT_DEPTH") ? atoi(getenv("PDEODE_INIT_DEPTH")) : 4;
+        if (depth <= 2) {
+            if (a.BS == 64) return launch_init_bulk<64, 2>(a, st);
+            if (a.BS == 128) return launch_init_bulk<128, 2>(a, st);
+            return launch_init_bulk<256, 2>(a, st);
+        }
+        if (a.BS == 64) return launch_init_bulk<64, 4>(a, st);
+        if (a.BS == 128) return launch_init_bulk<128, 4>(a, st);
+        return launch_init_bulk<256, 4>(a, st);
     }
     return launch_stencil<MODE_INIT>(a, st);
 }
@@ -2607,7 +2656,9 @@ cudaError_t launch_xtail(double *x, const double *p, const DevScal *S, long long
 }
 
 cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st) {
-    k_solvec<<<flat_blocks(a.n2), 256, 0, st>>>(a);
+    static const int unroll = getenv("PDEODE_SOLVEC_UNROLL") ? atoi(getenv("PDEODE_SOLVEC_UNROLL")) : 2;
+    if (unroll >= 2) k_solvec<2><<<flat_blocks((a.n2 + 1) / 2), 256, 0, st>>>(a);
+    else k_solvec<1><<<flat_blocks(a.n2), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

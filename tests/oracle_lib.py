@@ -92,6 +92,8 @@ def load(omp=False):
     lib.oracle_set_state.argtypes = [C.c_void_p, _dp, _dp]
     lib.oracle_get_state.restype = None
     lib.oracle_get_state.argtypes = [C.c_void_p, _dp, _dp]
+    lib.oracle_set_mnew.restype = None
+    lib.oracle_set_mnew.argtypes = [C.c_void_p, _dp]
     lib.oracle_get_mnew.restype = None
     lib.oracle_get_mnew.argtypes = [C.c_void_p, _dp]
     lib.oracle_set_maxit.restype = None
@@ -134,6 +136,9 @@ class Oracle:
         M = np.empty(self.n); Cc = np.empty(self.n)
         self.lib.oracle_get_state(self.h, M, Cc)
         return M, Cc
+
+    def set_mnew(self, x):
+        self.lib.oracle_set_mnew(self.h, np.ascontiguousarray(x, np.float64).ravel())
 
     def get_mnew(self):
         x = np.empty(self.n)
@@ -226,11 +231,29 @@ def replay_step(lib, p, row, col, M, Cc, Mnew):
         lib.oracle_gen_matrix(Mprev, Cc, A, ioff, rhs, row, col, C.byref(p))
         nit = C.c_longlong(100 * n); e1 = C.c_double(p.e1); e2 = C.c_double(p.e2)
         st = C.c_int(); scr = np.zeros(3 * n); tr = (CgTrace * cap)()
+        x0 = Mnew.copy()
         lib.oracle_solve_ls_diag(n, 5, ioff, A, Mnew, rhs, C.byref(nit), C.byref(e1), C.byref(e2),
                                  C.byref(st), scr, C.cast(tr, C.c_void_p), cap)
         k = int(nit.value)
         nits.append(k)
         hits = [i + 1 for i in range(min(k, cap) - 1) if tr[i].err2 < NEAR * p.e2 * tr[i].normx]
+        if 0 < k <= cap and tr[k - 1].err2 * NEAR > p.e2 * tr[k - 1].normx:
+            # The mirror case: the reference itself stopped with err2 within NEAR of the threshold
+            # (from below).  Another summation order may miss that stop; where it can stop next is
+            # read off the reference's own CG with the stop rule switched off (e2 = 0, the same
+            # start vector): every later iteration within NEAR of the threshold, up to and
+            # including the first one clearly below it.
+            x2 = x0.copy()
+            nit2 = C.c_longlong(min(k + 64, cap)); e1b = C.c_double(p.e1); e2b = C.c_double(0.0)
+            tr2 = (CgTrace * cap)()
+            lib.oracle_solve_ls_diag(n, 5, ioff, A, x2, rhs, C.byref(nit2), C.byref(e1b), C.byref(e2b),
+                                     C.byref(st), scr, C.cast(tr2, C.c_void_p), cap)
+            for i in range(k, min(int(nit2.value), cap)):
+                thr = p.e2 * tr2[i].normx
+                if tr2[i].err2 < NEAR * thr:
+                    hits.append(i + 1)
+                if tr2[i].err2 * NEAR < thr:
+                    break
         near.append(hits if len(hits) <= NEAR_CAP else hits[:NEAR_CAP // 2] + hits[-NEAR_CAP // 2:])
         Cn = np.empty(n)
         lib.oracle_solve_c(Mprev, Mnew, Cprev, Cn, n, p.kappa, p.gama, p.tDel, p.gSelect)

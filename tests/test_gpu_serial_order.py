@@ -118,7 +118,10 @@ def test_default_order_against_reference_vectors(pb, engine_env, engine, name):
       * CG iterations per solve: the reference's count +-2 (BASELINE north_star), or +-2 around an
         iteration where the reference's own err2 came within 25 % of the stop threshold (CG:90)
         without crossing it -- a solve on such a plateau stops there under any other summation
-        order.  Asserted while the run is in lockstep with the reference, i.e. up to and
+        order -- and the mirror case: where the reference's own stop was that marginal (blobs33,
+        step 7: err2 = 0.987 x threshold at iteration 91, back above it until iteration 96), +-2
+        around the later near-threshold iterations of the reference's CG run on with the stop
+        rule off (oracle_lib.replay_step).  Asserted while the run is in lockstep with the reference, i.e. up to and
         including the first step in which a count differs: after that the two runs are different
         realisations of the same tolerance (the next solve starts 1e-8 away) and per-solve counts
         stop being comparable -- as between the reference's own serial and OpenMP builds.

@@ -32,6 +32,10 @@ def main():
     ap.add_argument("--stride", type=int, default=0)          # 0: 2 for <= 512, else 8
     ap.add_argument("--seed", type=int, default=7)
     ap.add_argument("--out", required=True)
+    ap.add_argument("--checkpoint", action="store_true",
+                    help="write <out>.ckpt.npz (trace so far + full state) at every frame and "
+                         "continue from it when it exists: (M, C) at a step boundary is the whole "
+                         "state of solveOrder2 (P:703-704 copy Mnew, Cnew over M, C)")
     args = ap.parse_args()
     import oracle_lib as ol
     row = col = args.grid
@@ -51,9 +55,29 @@ def main():
     nitmax = np.zeros(args.steps, np.int32)
     frames_at, hM, hC, mM, mC, fM, fC = [], [], [], [], [], [], []
     t0 = time.time()
-    for k in range(args.steps):
+    k0 = 0
+    ckpt = args.out + ".ckpt.npz"
+    if args.checkpoint and os.path.exists(ckpt):
+        z = np.load(ckpt)
+        k0 = int(z["k"])
+        count[:k0] = z["count"][:k0]; nitsum[:k0] = z["nitsum"][:k0]; nitmax[:k0] = z["nitmax"][:k0]
+        frames_at = list(z["frames_at"]); hM = list(z["hashM"]); hC = list(z["hashC"])
+        mM = list(z["meanM"]); mC = list(z["meanC"]); fM = list(z["M"]); fC = list(z["C"])
+        s.set_state(z["stateM"], z["stateC"])
+        s.set_mnew(z["stateM"])          # warm start of the next solve (P:714): Mnew == M here
+        t0 -= float(z["wall_s"])
+        print(f"continuing from step {k0}", file=sys.stderr, flush=True)
+    for k in range(k0, args.steps):
         if k % args.frame_every == 0:
             M, C = s.get_state()
+            if args.checkpoint and k > k0:
+                tmp = ckpt + ".tmp.npz"
+                np.savez_compressed(tmp, k=k, grid=row, stride=stride, impl=args.impl, info=info,
+                                    count=count, nitsum=nitsum, nitmax=nitmax,
+                                    frames_at=np.array(frames_at), hashM=np.array(hM), hashC=np.array(hC),
+                                    meanM=np.array(mM), meanC=np.array(mC), M=np.array(fM), C=np.array(fC),
+                                    stateM=M, stateC=C, wall_s=time.time() - t0)
+                os.replace(tmp, ckpt)
             frames_at.append(k)
             hM.append(hashlib.sha256(M.tobytes()).hexdigest())
             hC.append(hashlib.sha256(C.tobytes()).hexdigest())
