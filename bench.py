@@ -318,6 +318,15 @@ def quiet_stdout():
     os.dup2(2, 1)
 
 
+_T0 = time.perf_counter()
+
+
+def log(msg):
+    """Progress on stderr (the one JSON line owns stdout)."""
+    sys.stderr.write(f"[bench {time.perf_counter() - _T0:7.1f} s] {msg}\n")
+    sys.stderr.flush()
+
+
 def emit(obj):
     sys.stdout.flush()
     line = (json.dumps(obj) + "\n").encode()
@@ -427,6 +436,8 @@ def main():
         return float(t.item()), its
 
     # ---- resident-state throughput (inputs already in HBM) ----
+    if rank == 0:
+        log(f"context and host fields ready ({row}x{col}, {world} rank(s), exchange {exchange})")
     s.set_state_ptr(Mh.data_ptr(), Ch.data_ptr())
 
     pic_total = [0]
@@ -449,6 +460,8 @@ def main():
     clocks = clk.stop() if rank == 0 else None
     launches = s.launch_count() - l0
     value = n * it_res / t_res
+    if rank == 0:
+        log(f"resident: {args.steps} steps, {it_res} CG iterations, {1e3 * t_res / args.steps:.2f} ms per step, {value:.4g} {UNIT}")
 
     # ---- N > 1: the slabs, gathered on rank 0, against the same steps on ONE rank ----
     parity = None
@@ -485,6 +498,8 @@ def main():
                       "against": "the same %d steps on a 1-rank context on rank 0's GPU" % nsteps_done}
         barrier()
 
+    if rank == 0 and parity is not None:
+        log(f"parity against one rank: {parity}")
     # ---- end to end through the C ABI with host buffers ----
     e2e = None
     if not args.no_e2e:
@@ -503,6 +518,8 @@ def main():
                "note": "every step: pdeode_set_state (pinned host -> device), pdeode_step, "
                        "pdeode_get_state, pdeode_mass; set_state restarts the CG warm start"}
 
+    if rank == 0 and e2e is not None:
+        log(f"e2e: {e2e['ms_per_step']:.2f} ms per step, {e2e['value']:.4g} {UNIT}")
     # ---- shipped-parameter run: wall time per step ----
     default_ms = None
     if world == 1 and args.grid <= 4096:
@@ -549,6 +566,8 @@ def main():
                     "frac": 96 * n / (ks["cg_spmv"]["ms"] + ks["cg_update"]["ms"]) / 1e6 / peak}}
     s.close()
     del Mh, Ch, Mout, Cout
+    if rank == 0:
+        log(f"shipped parameters: {default_ms}; roofline: {None if roof is None else {k: v for k, v in roof.items() if k in ('kernel', 'achieved', 'frac')}}")
 
     # ---- the north-star strong-scaling point, in the same run: 16384 x 16384 over `world` GPUs ----
     strong = None
@@ -563,16 +582,19 @@ def main():
             ("shipped_beta4", dict(), 0.9, None, 3, 3),
             # SURVEY config 4, the stiff regime of README.md:42-44 / P:471: beta = 6, height 0.95.
             # Its solves run for 1e4 .. 1e6 iterations, so a step is cut to its first Picard
-            # iterate (eSoln above the residual sum, P:706) and --strong-cg-cap CG iterations
-            # (CG:88) of the run's first step, rebuilt on the device every time: the same
-            # iterations at every N
-            ("stiff_beta6", dict(beta=6, eSoln=1.5), 0.95, args.strong_cg_cap, 3, 3),
+            # iterate (pdeode_set_picard_cap(0): the truncated iterate is far from converged --
+            # mean |M - Mnew| of order 100 at this size -- and the Picard loop would otherwise
+            # go on for hours) and --strong-cg-cap CG iterations (CG:88) of the run's first
+            # step, rebuilt on the device every time: the same iterations at every N
+            ("stiff_beta6", dict(beta=6), 0.95, args.strong_cg_cap, 3, 3),
         )
         for name, over, height, cap, w16, k16 in runs:
             p16 = pb.default_params(g16, **over)
             s16 = pb.Solver(g16, g16, p16, device=local, rank=rank, nranks=world, nccl_id=fresh_nccl_id())
             s16.set_stream(stream.cuda_stream)
             s16.set_maxit(cap if cap is not None else 10 * args.cg_cap)
+            if cap is not None:
+                s16.set_picard_cap(0)
             s16.set_initial_condition(1, args.depth, height)      # built on the device (P:279-288)
 
             def step16():
@@ -598,6 +620,8 @@ def main():
             if not (np.isfinite(mM) and np.isfinite(mC)):
                 strong[name]["invalid"] = "non-finite state"
             s16.close()
+            if rank == 0:
+                log(f"16384^2 {name}: {strong[name]['ms_per_step']:.1f} ms per step, {it16} CG iterations, {strong[name]['value']:.4g} {UNIT}")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
@@ -609,6 +633,8 @@ def main():
                           "-O3 -fopenmp as runAll_paral.sh:6)" if kind == "reference" else
                           "oracle port with OpenMP")}
 
+    if rank == 0 and cpu is not None:
+        log(f"cpu baseline: {cpu['value']:.4g} {UNIT} on {cpu['cores']} threads ({cpu['kind']})")
     if rank == 0:
         cfg = workload_config(args, world)         # the same dict the reference arm prints
         exchange_txt = {"single": "none (one GPU)",

@@ -110,11 +110,14 @@ int pdeode_set_stream(pdeode_ctx *ctx, void *cuda_stream);
 int pdeode_set_state(pdeode_ctx *ctx, const double *M, const double *C);
 
 /* setInitialConditions on the device (P:262-439), instead of
- * generating the fields on the host and uploading them.  MinitialCond 1-6 and
- * 8-10; 7 (one random draw per cell, in sequence) is not offered -- generate it
- * on the host and use pdeode_set_state.  px, py: the npts inoculation points of
- * cases 4, 5, 9, 10 (the caller's random draws xr, yr of P:312-313, 332-334,
- * 409-414, or the spacing of P:393 with py = 0); ignored otherwise.  Same
+ * generating the fields on the host and uploading them.  MinitialCond 1-10.
+ * px, py: the npts inoculation points of cases 4, 5, 9, 10 (the caller's random
+ * draws xr, yr of P:312-313, 332-334, 409-414, or the spacing of P:393 with
+ * py = 0); ignored for 1-3, 6, 8.  Case 7 (P:365-372: one random_number per
+ * cell, in cell order) takes npts = 1 and the 64-bit seed of the caller's
+ * generator as px[0] = seed mod 2^32, py[0] = seed div 2^32: cell i gets draw
+ * number i of splitmix64(seed) -- the host program's stand-in for
+ * random_number, whose k-th draw depends on seed + k * constant only.  Same
  * values as the reference's loops, cell by cell; case 5's normalisation sums
  * in parallel.  Resets the CG warm start like pdeode_set_state. */
 int pdeode_set_initial_condition(pdeode_ctx *ctx, int MinitialCond, double depth, double height,
@@ -166,6 +169,12 @@ int pdeode_peak(pdeode_ctx *ctx, double *peak, double *height, double *intfac);
 
 /* CG iteration cap; default 100*n (P:707).  < 0 restores the default. */
 int pdeode_set_maxit(pdeode_ctx *ctx, long long maxit);
+
+/* Picard iterate cap of a time step; default 10000 (P:732: `if (countIters > 10000)` ends the
+ * run).  A step gives up with PDEODE_ERR_PICARD_CAP -- counts filled in, state = the last
+ * iterate -- once countIters > cap, so cap = 0 makes a step exactly one Picard iterate (used
+ * by bench.py to time a fixed number of CG iterations of a stiff solve).  < 0 restores 10000. */
+int pdeode_set_picard_cap(pdeode_ctx *ctx, int cap);
 
 /* Per-Picard-iterate record of the last pdeode_step: CG iterations of each
  * solve and (diffC, diffM) pairs (P:725-726); at most cap entries.  Returns

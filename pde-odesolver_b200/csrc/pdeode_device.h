@@ -147,6 +147,7 @@ struct PersistArgs {
     int nstrips, nchunks;  // G = nstrips * nchunks CTAs, one tile each
     int serial;            // PDEODE_SUM_ORDER=serial: CTA 0 re-does every sum in cell order
     double *ser_out;       // [2][SER_MAXJ] results of those sums
+    int prefetch;          // rows of a tile pulled into L2 while waiting for a grid-wide sum (0: none)
 };
 
 // What one whole-step launch (k_step_persist) reports back: the quantities
@@ -198,6 +199,7 @@ struct StepArgs {
     unsigned long long seq;
     int serial;            // PDEODE_SUM_ORDER=serial: CTA 0 re-does every sum in cell order
     double *ser_out;       // [2][SER_MAXJ] results of those sums
+    int prefetch;          // pull the next phase's rows into L2 while waiting for a grid-wide sum
 };
 
 struct UpdateArgs {
@@ -282,6 +284,7 @@ struct LaunchCfg {
     int kb_reverse;        // K_B sweeps against K_A's direction
     int defer_x;           // 88-byte iteration: x += alfa p deferred into the next SpMV kernel
     int persist_defer;     // the same inside the persistent solve (measured slower: default 0)
+    int persist_prefetch;  // L2 prefetch across the grid-wide sums, rows per tile: -1 = auto (multi-GPU only)
     int TR_x;              // rows per CTA of the 88-byte SpMV kernel (its optimum is lower)
     int i_BS, i_TR;        // launch shape of the INIT kernel (two IEEE divides per cell: it
                            // wants more warps per SM than the SpMV does)

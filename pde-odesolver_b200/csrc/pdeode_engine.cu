@@ -53,6 +53,7 @@ struct pdeode_ctx {
     long long n_local = 0;        // rows * col
     size_t arr_doubles = 0;       // allocation size of one array
     long long maxit = 0, maxit_default = 0;
+    int picard_cap = PICARD_CAP;               // P:732; pdeode_set_picard_cap
 
     // field buffers: three M, three C (prev / current / new rotate), work arrays
     static constexpr int NARR = 12;
@@ -230,6 +231,16 @@ StencilArgs stencil_args(pdeode_ctx *c) {
     return a;
 }
 
+// Rows per tile the persistent solve pulls into L2 while a grid-wide sum is under way.
+int persist_prefetch_rows(const pdeode_ctx *c) {
+    if (c->cfg.persist_prefetch >= 0) return c->cfg.persist_prefetch;
+    if (!multi(c)) return 0;
+    const long long G = (long long)c->cfg.p_nstrips * c->cfg.p_nchunks;
+    const long long per_row = 3LL * 2 * c->cfg.p_BS * 8;          // three arrays, one strip wide
+    const long long rows = (40LL << 20) / std::max<long long>(1, G * per_row);
+    return (int)std::min<long long>(rows, 1 << 20);
+}
+
 // one CG iteration: CG:55-90
 int cg_iteration(pdeode_ctx *c, double *x) {
     const int mode = sums_mode(c);
@@ -330,6 +341,7 @@ int solve(pdeode_ctx *c, const double *x0, double *x, int solve_idx, long long *
         pa.slots = c->persist_slots; pa.counter = c->persist_counter; pa.gen0 = c->persist_gen;
         pa.nstrips = c->cfg.p_nstrips; pa.nchunks = c->cfg.p_nchunks;
         pa.serial = c->serial ? 1 : 0; pa.ser_out = c->ser_out;
+        pa.prefetch = persist_prefetch_rows(c);
         CK(launch_cg_persist(pa, c->cfg.p_BS, c->stream));
         c->launches++;
         // no wait here: the C update queues right behind, and the caller reads the
@@ -1046,8 +1058,9 @@ int pdeode_set_initial_condition(pdeode_ctx *c, int ic, double depth, double hei
     GROUP(c, group_run(c, [&](int, pdeode_ctx *m) {
         return pdeode_set_initial_condition(m, ic, depth, height, npts, px, py);
     }));
-    if (!c || ic < 1 || ic > 10 || ic == 7) return PDEODE_ERR_ARG;
-    const bool pts = (ic == 4 || ic == 5 || ic == 9 || ic == 10);
+    if (!c || ic < 1 || ic > 10) return PDEODE_ERR_ARG;
+    if (ic == 7 && (npts != 1 || !px || !py)) return PDEODE_ERR_ARG;   // the generator's seed, see the header
+    const bool pts = (ic == 4 || ic == 5 || ic == 7 || ic == 9 || ic == 10);
     if (pts && (npts < 0 || (npts > 0 && (!px || !py)))) return PDEODE_ERR_ARG;
     CK(cudaSetDevice(c->device));
     c->iM = c->iMprev = 0; c->iC = c->iCprev = 0; c->iMnew = 1;
@@ -1203,7 +1216,7 @@ int step_whole(pdeode_ctx *c, int nsteps) {
     a.stamps = c->step_stamps ? 1 : 0;
     a.nstrips = c->cfg.s_nstrips; a.nchunks = c->cfg.s_nchunks; a.cw = c->cfg.s_cw;
     a.eSoln = c->params.eSoln;
-    a.picard_cap = PICARD_CAP;
+    a.picard_cap = c->picard_cap;
     a.out = c->step_out;
     a.serial = c->serial ? 1 : 0; a.ser_out = c->ser_out;
     c->iMprev = c->iM; c->iCprev = c->iC;            // P:703-704
@@ -1375,7 +1388,7 @@ int pdeode_step(pdeode_ctx *c, int *countIters, long long *nitSum, long long *ni
         // where pdeode_mass adds in cell order itself)
         c->sums_valid = !c->serial;
         c->sumM = c->snap[0].s.sumM; c->sumC = c->snap[0].s.sumC;
-        if (count > PICARD_CAP) {                    // P:732
+        if (count > c->picard_cap) {                 // P:732
             if (countIters) *countIters = count;
             if (nitSum) *nitSum = sum;
             if (nitMax) *nitMax = mx;
@@ -1509,6 +1522,13 @@ int pdeode_set_maxit(pdeode_ctx *c, long long maxit) {
     return PDEODE_OK;
 }
 
+int pdeode_set_picard_cap(pdeode_ctx *c, int cap) {
+    if (!c) return PDEODE_ERR_ARG;
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) { return pdeode_set_picard_cap(m, cap); }));
+    c->picard_cap = cap >= 0 ? cap : PICARD_CAP;
+    return PDEODE_OK;
+}
+
 int pdeode_last_step_trace(pdeode_ctx *c, long long *nit_per_solve, double *diffs, int cap,
                            int *count) {
     if (!c) return PDEODE_ERR_ARG;
@@ -1583,19 +1603,21 @@ int pdeode_engine_info(const pdeode_ctx *c, char *buf, int len) {
     if (c->group) {
         char one[512];
         const int rc = pdeode_engine_info(c->group->m[0], one, (int)sizeof one);
-        snprintf(buf, (size_t)len, "%s gpus=%d(one process)", one, c->group->n);
+        snprintf(buf, (size_t)len, "%s gpus=%d(one-process)", one, c->group->n);
         return rc;
     }
     snprintf(buf, (size_t)len,
              "spmv=%s BS=%d TR=%d depth=%d init_BS=%d init_TR=%d persist=%d persist_ctas=%d "
-             "defer_x=%d kb_reverse=%d whole_step=%d step_BS=%d step_ctas=%d exchange=%s sum_order=%s",
+             "defer_x=%d kb_reverse=%d whole_step=%d step_BS=%d step_ctas=%d exchange=%s sum_order=%s "
+             "persist_prefetch=%d",
              c->cfg.variant == 1 ? "bulk-async" : "register-staged", c->cfg.BS, c->cfg.TR,
              c->cfg.DEPTH, c->cfg.i_BS, c->cfg.i_TR, c->cfg.persist,
              c->cfg.p_nstrips * c->cfg.p_nchunks,
              (c->cfg.persist && sums_mode(c) != SUMS_RAW ? c->cfg.persist_defer != 0 : defer_x(c)) ? 1 : 0,
              c->cfg.kb_reverse, c->cfg.whole_step, c->cfg.s_BS,
              c->cfg.s_nstrips * c->cfg.s_nchunks,
-             !multi(c) ? "none" : (c->peer ? "peer" : "nccl"), c->serial ? "serial" : "tree");
+             !multi(c) ? "none" : (c->peer ? "peer" : "nccl"), c->serial ? "serial" : "tree",
+             persist_prefetch_rows(c));
     return PDEODE_OK;
 }
 

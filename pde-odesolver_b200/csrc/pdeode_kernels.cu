@@ -52,12 +52,47 @@ __device__ __forceinline__ double powi(double x, int m) {
     return (m < 0) ? 1.0 / y : y;
 }
 
+// The same multiplications in the same order with the exponent known at compile time: the
+// square-and-multiply loop unrolls into two to four DMULs (a product with the initial 1.0 is
+// exact, so dropping it changes no bit).
+template <int M_>
+__device__ __forceinline__ double powi_c(double x) {
+    static_assert(M_ >= 0, "non-negative exponents only");
+    unsigned int n = (unsigned int)M_;
+    double y = (n & 1u) ? x : 1.0;
+#pragma unroll
+    for (int k = 0; k < 5; ++k) {
+        n >>= 1;
+        if (n == 0u) break;
+        x = x * x;
+        if (n & 1u) y *= x;
+    }
+    return y;
+}
+// Exponents 0..8 (the shipped file has alpha = beta = 4, README.md:42-44 goes to 6) take the
+// unrolled form -- one uniform jump instead of a shift / test / branch per bit; anything else
+// runs the loop.
+__device__ __forceinline__ double powi_fast(double x, int m) {
+    switch (m) {
+    case 0: return powi_c<0>(x);
+    case 1: return powi_c<1>(x);
+    case 2: return powi_c<2>(x);
+    case 3: return powi_c<3>(x);
+    case 4: return powi_c<4>(x);
+    case 5: return powi_c<5>(x);
+    case 6: return powi_c<6>(x);
+    case 7: return powi_c<7>(x);
+    case 8: return powi_c<8>(x);
+    default: return powi(x, m);
+    }
+}
+
 // P:464-472
 __device__ __forceinline__ double dfunc(double M, const NumParams &np) {
     double d = 0.0;
     if (np.dSelect == 1) d = np.delta;
-    else if (np.dSelect == 2) d = np.delta * powi(M, np.alpha);
-    else if (np.dSelect == 3) d = np.delta * powi(M, np.alpha) / powi(1.0 - M, np.beta);
+    else if (np.dSelect == 2) d = np.delta * powi_fast(M, np.alpha);
+    else if (np.dSelect == 3) d = np.delta * powi_fast(M, np.alpha) / powi_fast(1.0 - M, np.beta);
     return d;
 }
 
@@ -452,6 +487,23 @@ __device__ __forceinline__ void peer_post(const PeerComm &pc, unsigned long long
     }
 }
 
+// The same from a whole warp that holds the sums in every lane: lane r stores into rank r's
+// comm block, so the ranks' six words leave side by side instead of one rank after the other.
+__device__ __forceinline__ void peer_post_lanes(const PeerComm &pc, unsigned long long phase,
+                                                double a, double b, double c) {
+    const int r = threadIdx.x & 31;
+    if (r >= pc.nranks) return;
+    const int slot = (int)(phase % PEER_SLOTS);
+    unsigned long long *w = reinterpret_cast<unsigned long long *>(pc.peer_slots[r]) +
+                            ((size_t)slot * PEER_MAX_RANKS + pc.rank) * PEER_VALS;
+    st_relaxed_sys(w, ll_word((unsigned int)__double2loint(a), phase));
+    st_relaxed_sys(w + 1, ll_word((unsigned int)__double2hiint(a), phase));
+    st_relaxed_sys(w + 2, ll_word((unsigned int)__double2loint(b), phase));
+    st_relaxed_sys(w + 3, ll_word((unsigned int)__double2hiint(b), phase));
+    st_relaxed_sys(w + 4, ll_word((unsigned int)__double2loint(c), phase));
+    st_relaxed_sys(w + 5, ll_word((unsigned int)__double2hiint(c), phase));
+}
+
 // ---------------------------------------------------------------- D(M)
 
 // One IEEE divide and two integer powers per cell: a long dependent chain.  Every thread keeps
@@ -736,6 +788,11 @@ __device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned by
             "r"(smem_u32(dst)),
         "l"(src), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
+}
+
+// Hint: bring [src, src + bytes) into L2 (no destination, no completion to wait for).
+__device__ __forceinline__ void bulk_prefetch_l2(const void *src, unsigned bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(src), "r"(bytes) : "memory");
 }
 
 // Same arithmetic as k_stencil<MODE_CG>, different data movement: one producer
@@ -1378,10 +1435,11 @@ __device__ __forceinline__ bool persist_allsum(double &a, double &b, double &c, 
             x += u.x; y += u.y; z += w.x;
         }
         __syncthreads();                 // block_sum3's scratch is free again
-        block_sum3(x, y, z, sm);
-        if (tid == 0) {
-            if (peer) peer_post(pc, ph, x, y, z);
-            else { s_tot[0] = x; s_tot[1] = y; s_tot[2] = z; }
+        block_sum3(x, y, z, sm);                 // totals in every lane of warp 0
+        if (peer) {
+            if (tid < 32) peer_post_lanes(pc, ph, x, y, z);
+        } else if (tid == 0) {
+            s_tot[0] = x; s_tot[1] = y; s_tot[2] = z;
         }
     }
     if (peer) return peer_wait_sums(pc, ph, S, a, b, &c);     // barriers inside
@@ -1447,6 +1505,10 @@ k_cg_persist(const PersistArgs A) {
     const int i_end = (int)((long long)(chunk + 1) * g.rows / A.nchunks);
     const int j0 = jt + 2 * tid;
     const bool worker = (tid < BS) && (j0 < g.P);
+    const unsigned pf_bytes = (unsigned)max(0, min(TC, g.P - jt)) * 8u;   // a row of my strip
+    // the first A.prefetch rows of my tile (what all CTAs pull together has to fit L2 next to
+    // the rows the running phase keeps hot)
+    const int pf_rows = pf_bytes ? min(A.prefetch, i_end - i_begin) : 0;
 
     if (tid == 0) R.init_barriers();
     __syncthreads();
@@ -1493,6 +1555,17 @@ k_cg_persist(const PersistArgs A) {
                                     defer ? A.x : nullptr, alfa, &acc2);
         }
         K += (i_end - i_begin) + 2;
+        // While the sum is under way (one rank: ~3 us; all ranks over NVLink: 6-7 us) HBM would
+        // idle.  The next phase's loads need none of the scalars, so the rows of my tile that
+        // phase B reads and that are not L2-hot from this phase (x, r; p and q were just written)
+        // are pulled into L2 now (the first pf_rows of them), one row segment per thread, in the
+        // order they will be used.
+        if (pf_rows)
+            for (int t = tid; t < pf_rows; t += blockDim.x) {
+                const long long o = (long long)(i_begin + t) * g.P + jt;
+                if (!defer) bulk_prefetch_l2(A.x + o, pf_bytes);
+                bulk_prefetch_l2(a.r + o, pf_bytes);
+            }
         ++ph; ++gen;
         if (!persist_allsum(acc0, acc1, acc2, A.slots, A.counter, gen, G, peer, false, false, a.pc, ph, S, sm, s_tot)) {
             stop = -1;                       // an exchange timed out (DevScal::error is set): leave
@@ -1516,9 +1589,23 @@ k_cg_persist(const PersistArgs A) {
         }
         // ---- phase B: my own cells (the ones whose p and q I just wrote)
         double rr = 0.0, xn = 0.0;
+        // the slab's last row goes first: its stores into the lower neighbour GPU then have the
+        // whole phase to land before the system-wide fence that precedes my arrival at the sum
+        // (the first row, for the upper neighbour, is first anyway)
+        const bool last_first = dn && i_end == g.rows && i_end - i_begin > 1;
+        const int i_hi = last_first ? i_end - 1 : i_end;
         if (worker && defer) {
             long long off = (long long)i_begin * g.P + j0;
-            for (int i = i_begin; i < i_end; ++i, off += g.P) {
+            if (last_first) {
+                const long long o = (long long)(i_end - 1) * g.P + j0;
+                double2 r2 = ld2(a.r + o);
+                const double2 q2 = ld2(a.q + o);
+                r2.x = r2.x - alfa * q2.x; r2.y = r2.y - alfa * q2.y;  // CG:81
+                st2(a.r + o, r2);
+                st2(dn + j0, r2);
+                rr += r2.x * r2.x; rr += r2.y * r2.y;
+            }
+            for (int i = i_begin; i < i_hi; ++i, off += g.P) {
                 double2 r2 = ld2(a.r + off);
                 const double2 q2 = ld2(a.q + off);
                 r2.x = r2.x - alfa * q2.x; r2.y = r2.y - alfa * q2.y;  // CG:81
@@ -1540,8 +1627,12 @@ k_cg_persist(const PersistArgs A) {
                 rr += r2.x * r2.x; rr += r2.y * r2.y;
                 xn += x2.x * x2.x; xn += x2.y * x2.y;
             };
+            if (last_first) {
+                const long long o = (long long)(i_end - 1) * g.P + j0;
+                upd(i_end - 1, o, ld2(A.x + o), ld2(p_out + o), ld2(a.r + o), ld2(a.q + o));
+            }
             int i = i_begin;
-            for (; i + 1 < i_end; i += 2, off += 2 * g.P) {          // two rows in flight
+            for (; i + 1 < i_hi; i += 2, off += 2 * g.P) {           // two rows in flight
                 const long long o1 = off + g.P;
                 const double2 xa = ld2(A.x + off), pa = ld2(p_out + off);
                 const double2 ra = ld2(a.r + off), qa = ld2(a.q + off);
@@ -1550,9 +1641,19 @@ k_cg_persist(const PersistArgs A) {
                 upd(i, off, xa, pa, ra, qa);
                 upd(i + 1, o1, xb, pb, rb, qb);
             }
-            if (i < i_end) upd(i, off, ld2(A.x + off), ld2(p_out + off), ld2(a.r + off), ld2(a.q + off));
+            if (i < i_hi) upd(i, off, ld2(A.x + off), ld2(p_out + off), ld2(a.r + off), ld2(a.q + off));
             asm volatile("fence.proxy.async;" ::: "memory");         // next phase A reads r via bulk copies
         }
+        // the same for phase A of the next iteration: d, ac and the direction just written
+        // (r is L2-hot: phase B stored it a moment ago)
+        if (pf_rows)
+            for (int t = tid; t < pf_rows; t += blockDim.x) {
+                const long long o = (long long)(i_begin + t) * g.P + jt;
+                bulk_prefetch_l2(a.d + o, pf_bytes);
+                bulk_prefetch_l2(a.ac + o, pf_bytes);
+                bulk_prefetch_l2(p_out + o, pf_bytes);
+                if (defer) bulk_prefetch_l2(A.x + o, pf_bytes);
+            }
         // only CTAs that stored into a neighbour GPU need the system-wide fence
         const bool wrote_peer = (up && i_begin == 0) || (dn && i_end == g.rows);
         double zz = 0.0;
@@ -2207,7 +2308,10 @@ __global__ void __launch_bounds__(128) k_rowmeans(GridDesc g, const double *__re
 // values are the host's bit for bit.  px / py hold the points: the random
 // draws of P:312-313,332-334,409-414 (made by the caller's seeded generator)
 // or the spacing formula of P:393.  Case 7 draws one random number per cell
-// in sequence and stays on the host.
+// in sequence (P:365-372); the cells that draw are a prefix 1..K of the cell order (the test
+// (double)i * xDel / col <= depth is monotone in i), so cell i takes draw number i of the
+// caller's generator -- splitmix64, whose draw k depends on seed + k * constant only.  The seed
+// arrives as px[0] (low 32 bits) and py[0] (high 32 bits).
 __global__ void __launch_bounds__(256) k_init_cond(GridDesc g, int ic, double depth, double height,
                                                    double xDel, int npts,
                                                    const double *__restrict__ px,
@@ -2256,6 +2360,16 @@ __global__ void __launch_bounds__(256) k_init_cond(GridDesc g, int ic, double de
         } else if (ic == 6) {                                             // P:356-362
             const long long x = (i - 1) / g.col;
             if (x * xDel <= depth) m = height;
+        } else if (ic == 7) {                                             // P:365-372
+            if ((double)i * xDel / g.col <= depth) {
+                const unsigned long long seed =
+                    ((unsigned long long)py[0] << 32) | (unsigned long long)px[0];
+                unsigned long long z = seed + (unsigned long long)i * 0x9E3779B97F4A7C15ull;
+                z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+                z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+                z ^= z >> 31;
+                m = ((double)(z >> 11) * (1.0 / 9007199254740992.0)) * 0.2;
+            }
         } else if (ic == 8) {                                             // P:375-387
             m = (double)i / (double)n / 4.0;
             if (m >= 0.1) m = 0;
@@ -2470,6 +2584,11 @@ LaunchCfg launch_config(const GridDesc &g) {
     // sweep at 4096^2: the 88-byte kernel runs 0.183 ms at 32 rows per CTA, 0.194 ms at 64
     c.TR_x = c.TR > 32 ? 32 : c.TR;
     if (const char *e = getenv("PDEODE_PERSIST_DEFER")) c.persist_defer = atoi(e) != 0;
+    // L2 prefetch of the next phase's rows while a grid-wide sum is under way, in rows per tile:
+    // -1 = as a slab of a multi-GPU run only (the all-rank sum takes 6-7 us and the slab does
+    // not fit L2), as many rows as fit a 40 MB budget over all CTAs
+    c.persist_prefetch = -1;
+    if (const char *e = getenv("PDEODE_PERSIST_PREFETCH")) c.persist_prefetch = atoi(e) > 0 ? atoi(e) : 0;
     if (const char *e = getenv("PDEODE_DEFER_X")) c.defer_x = atoi(e) != 0;
     // INIT (sweep at 4096^2): bulk BS 128 x 32 rows 0.200 ms, BS 256 x 64 rows 0.322 ms
     c.i_BS = c.BS > 128 ? 128 : c.BS;

@@ -205,6 +205,12 @@ bool inoculation_points(const RunParams &p, uint64_t seed, std::vector<double> &
             if (k > np) yr = yr + 0.9;
             py.push_back(yr);
         }
+    } else if (ic == 7) {
+        // one draw per cell, in cell order (P:365-372): the generator is a counter (splitmix64:
+        // draw k is a function of seed + k * constant), so the device needs only the seed --
+        // handed over as two 32-bit halves, each exact in a double
+        px.push_back((double)(seed & 0xFFFFFFFFull));
+        py.push_back((double)(seed >> 32));
     } else {
         return false;
     }
@@ -740,10 +746,10 @@ int run_program(FILE *in, FILE *con, const Stepper &st, int device, const std::s
     else seed = (uint64_t)std::chrono::system_clock::now().time_since_epoch().count();  // clock, as init_random_seed.f90:11
     std::vector<double> C, M;
     // Build the fields on the device when the stepper offers it (all cases but the
-    // per-cell random one, 7, and the restart, 11); PDEODE_HOST_IC=1 forces the host loops.
+    // restart, 11); PDEODE_HOST_IC=1 forces the host loops.
     DeviceIc dic;
     const int icn = p.MinitialCond;
-    const bool use_dic = st.set_initial_condition && st.frame_size && icn >= 1 && icn <= 10 && icn != 7 &&
+    const bool use_dic = st.set_initial_condition && st.frame_size && icn >= 1 && icn <= 10 &&
                          !(getenv("PDEODE_HOST_IC") && getenv("PDEODE_HOST_IC")[0] == '1');
     if (use_dic) {
         dic.ic = icn; dic.depth = p.depth; dic.height = p.height;

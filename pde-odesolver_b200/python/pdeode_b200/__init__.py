@@ -88,6 +88,7 @@ def _lib():
         "pdeode_mass": [vp, dp, dp],
         "pdeode_peak": [vp, dp, dp, dp],
         "pdeode_set_maxit": [vp, C.c_longlong],
+        "pdeode_set_picard_cap": [vp, C.c_int],
         "pdeode_last_step_trace": [vp, llp, dp, C.c_int, ip],
         "pdeode_cg_trace_enable": [vp, C.c_int],
         "pdeode_cg_trace_get": [vp, dp, C.c_int, ip],
@@ -262,6 +263,9 @@ class Solver:
         a, b, c = C.c_double(peak), C.c_double(height), C.c_double(intfac)
         self._ck(self.lib.pdeode_peak(self.h, C.byref(a), C.byref(b), C.byref(c)), "peak")
         return a.value, b.value, c.value
+
+    def set_picard_cap(self, cap):
+        self._ck(self.lib.pdeode_set_picard_cap(self.h, int(cap)), "set_picard_cap")
 
     def set_maxit(self, maxit):
         self._ck(self.lib.pdeode_set_maxit(self.h, int(maxit)), "set_maxit")

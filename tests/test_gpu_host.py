@@ -104,7 +104,7 @@ def test_ensemble_members_equal_single_runs(tmp_path):
             assert open(out / name).read() == open(single / name).read(), (k, name)
 
 
-@pytest.mark.parametrize("ic", [1, 2, 3, 4, 5, 6, 8, 9, 10])
+@pytest.mark.parametrize("ic", [1, 2, 3, 4, 5, 6, 7, 8, 9, 10])
 @pytest.mark.parametrize("row,col", [(65, 65), (129, 4), (70, 45)])
 def test_initial_conditions_built_on_device(ic, row, col):
     """pdeode_set_initial_condition against the host's setInitialConditions
@@ -144,3 +144,62 @@ def test_initial_conditions_built_on_device(ic, row, col):
     # NaN alike -- the reference's unguarded hazard S8 -- hence equal_nan)
     assert np.array_equal(a[0], b[0], equal_nan=True) and np.array_equal(a[1], b[1], equal_nan=True)
     s.close(); s2.close()
+
+
+@pytest.mark.parametrize("engine", ["whole-step", "kernels"])
+def test_final_state_and_restart_on_the_gpu(tmp_path, engine):
+    """SURVEY 8(f4) on the GPU stepper: PDEODE_FINAL_STATE writes the final fields (the print the
+    reference has commented out, P:747-755) and MinitialCond = 11 continues from such a file (the
+    restart the author could not get working, P:423-435).  41 steps in one go against 21 + 20
+    with a restart in between, through `echo FILE | pdeode_solver`; and the final state of the
+    uninterrupted GPU run against the oracle-driven host program's."""
+    ge.build_cuda(); ge.build_host(); ol.build_oracle()
+    exe = os.path.join(ge.BINDIR, "pdeode_solver")
+    base = open(os.path.join(DATA, "wave2d.txt")).read()
+    env = dict(os.environ, PDEODE_SEED="1", PDEODE_FINAL_STATE="final.dat")
+    env["PDEODE_WHOLE_STEP"] = "1" if engine == "whole-step" else "0"
+    if engine == "kernels":
+        env["PDEODE_PERSIST"] = "0"
+    dirs = {k: tmp_path / k for k in ("full", "a", "b", "cpu")}
+    for d in dirs.values():
+        d.mkdir()
+
+    def run(text, where, name):
+        f = tmp_path / name
+        f.write_text(text)
+        r = subprocess.run([exe], input=str(f) + "\n", text=True, capture_output=True, cwd=where,
+                           env=env, timeout=300)
+        return r
+
+    r = run(base, dirs["full"], "full.txt")
+    assert r.returncode == 0, r.stdout + r.stderr
+    first = base.replace("tEnd      = 0.04", "tEnd      = 0.0205").replace("nOuts     = 4", "nOuts     = 2")
+    assert first != base
+    r = run(first, dirs["a"], "first.txt")
+    assert r.returncode == 0, r.stdout + r.stderr
+    fin = np.loadtxt(dirs["a"] / "final.dat")
+    assert fin.shape == (129 * 4, 4)
+    os.rename(dirs["a"] / "final.dat", dirs["b"] / "initialCond.dat")
+    second = (base.replace("tEnd      = 0.04", "tEnd      = 0.0195").replace("nOuts     = 4", "nOuts     = 1")
+              .replace("MinitialCond = 1", "MinitialCond = 11"))
+    r = run(second, dirs["b"], "second.txt")
+    assert r.returncode == 0, r.stdout + r.stderr
+    assert "continue from initialCond.dat" in r.stdout
+    want = np.loadtxt(dirs["full"] / "final.dat")
+    got = np.loadtxt(dirs["b"] / "final.dat")
+    # same trajectory; the restart only loses the CG warm start of its first solve
+    assert np.array_equal(got[:, :2], want[:, :2])
+    assert np.allclose(got[:, 2:], want[:, 2:], rtol=0, atol=2e-7)
+    # the uninterrupted run's final state against the CPU oracle behind the same host program
+    os.environ["PDEODE_FINAL_STATE"] = "final.dat"
+    try:
+        assert run_oracle_program(str(tmp_path / "full.txt"), str(dirs["cpu"]), str(tmp_path / "cpu_console.txt")) == 0
+    finally:
+        del os.environ["PDEODE_FINAL_STATE"]
+    ref = np.loadtxt(dirs["cpu"] / "final.dat")
+    assert np.array_equal(ref[:, :2], want[:, :2])
+    assert np.allclose(ref[:, 2:], want[:, 2:], rtol=2e-7, atol=1e-12)
+    # a wrong-size file is refused (exit code 2), as on the CPU
+    (dirs["b"] / "initialCond.dat").write_text("0 0 0.5 1\n")
+    r = run(second, dirs["b"], "second.txt")
+    assert r.returncode == 2
