@@ -527,8 +527,24 @@ def main():
         s.set_state(Md, Cd)
         for _ in range(3):
             s.step()
-        t_d, it_d = timed(lambda: s.step()["nitSum"], 10)
-        default_ms = {"ms_per_step": 1e3 * t_d / 10, "cg_iterations_per_step": it_d / 10}
+        pic_d = [0]
+
+        def shipped_step():
+            r = s.step()
+            pic_d[0] += r["countIters"]
+            return r["nitSum"]
+
+        t_d, it_d = timed(shipped_step, 10)
+        # algorithmic bytes of a whole time step, SURVEY 8(d)'s per-kernel figures: D(M) once
+        # (16 B per cell), per Picard iterate centre diagonal + first residual (56) and C update +
+        # residuals (48), per CG iteration 96
+        by_d = 16.0 + 104.0 * pic_d[0] / 10 + 96.0 * it_d / 10
+        pk_d, _ = measured_peak()
+        default_ms = {"ms_per_step": 1e3 * t_d / 10, "cg_iterations_per_step": it_d / 10,
+                      "picard_iterates_per_step": pic_d[0] / 10,
+                      "bytes_per_cell_algorithmic": by_d,
+                      "GBps": by_d * n / (t_d / 10) / 1e9,
+                      "frac_of_measured_hbm_peak": by_d * n / (t_d / 10) / 1e9 / pk_d}
 
     # ---- roofline of the dominant kernel, timed live with CUDA events ----
     roof = None

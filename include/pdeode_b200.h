@@ -88,6 +88,14 @@ int pdeode_create_group(pdeode_ctx **ctx, int row, int col, const pdeode_params 
 
 int pdeode_destroy(pdeode_ctx *ctx);
 
+/* A new parameter set on an existing context of the same grid: what pdeode_destroy +
+ * pdeode_create with *p would give, without returning the device memory (the arrays, the
+ * launch configuration and, for several GPUs, the communicator and peer mappings stay).  The
+ * state is undefined afterwards: follow with pdeode_set_state / pdeode_set_initial_condition.
+ * CG and Picard caps return to their defaults.  For sweeps over numbered parameter files
+ * (.gitignore:34-35): pdeode_ensemble keeps one context per worker thread this way. */
+int pdeode_reconfigure(pdeode_ctx *ctx, const pdeode_params *p);
+
 /* Number of CUDA devices this process can use (0 and PDEODE_ERR_NODEVICE if none). */
 int pdeode_device_count(int *count);
 

@@ -963,6 +963,24 @@ int pdeode_create_group(pdeode_ctx **ctx, int row, int col, const pdeode_params 
     return group_create(ctx, row, col, p, ngpus, devices);
 }
 
+int pdeode_reconfigure(pdeode_ctx *c, const pdeode_params *p) {
+    if (!c || !p) return PDEODE_ERR_ARG;
+    GROUP(c, group_run(c, [&](int, pdeode_ctx *m) { return pdeode_reconfigure(m, p); }));
+    CK(cudaSetDevice(c->device));
+    CK(cudaStreamSynchronize(c->stream));
+    c->params = *p;
+    set_numparams(c, p);
+    for (int k = 0; k < MAX_PICARD_TRACE; ++k) c->pred[k] = (k == 0) ? 8 : 1;
+    c->maxit = c->maxit_default;
+    c->picard_cap = PICARD_CAP;
+    CK(cudaMemcpy(&c->S->maxit, &c->maxit, sizeof(long long), cudaMemcpyHostToDevice));
+    c->warm = false;
+    c->trace_count = 0;
+    c->mass_valid = false; c->sums_valid = false;
+    c->launches = 0;
+    return PDEODE_OK;
+}
+
 int pdeode_destroy(pdeode_ctx *c) {
     if (!c) return PDEODE_OK;
     GROUP(c, group_destroy(c));

@@ -2651,9 +2651,9 @@ LaunchCfg launch_config(const GridDesc &g) {
 
 int stream_blocks() { return g_num_sms * g_stream_ctas_per_sm; }
 
-static int flat_blocks(long long n2) {
+static int flat_blocks(long long n2, int ctas_per_sm = 0) {
     const long long want = (n2 + 255) / 256;
-    const long long cap = stream_blocks();
+    const long long cap = ctas_per_sm > 0 ? (long long)g_num_sms * ctas_per_sm : stream_blocks();
     return (int)(want < cap ? (want > 0 ? want : 1) : cap);
 }
 
@@ -2664,7 +2664,9 @@ int stencil_max_blocks(const GridDesc &g, int TR) {
 cudaError_t launch_diffcoef(const GridDesc &g, const NumParams &np, const double *M, double *d,
                             cudaStream_t st) {
     const long long n2 = (long long)g.rows * g.P / 2;
-    static const int unroll = getenv("PDEODE_DIFFCOEF_UNROLL") ? atoi(getenv("PDEODE_DIFFCOEF_UNROLL")) : 4;
+    // sweep at 4096^2 (profiles/r02_sweep_pointwise.jsonl): 0.104 ms with one or two double2 per
+    // thread in flight, 0.112 with four; 0.093 once the integer powers are unrolled (powi_fast)
+    static const int unroll = getenv("PDEODE_DIFFCOEF_UNROLL") ? atoi(getenv("PDEODE_DIFFCOEF_UNROLL")) : 2;
     if (unroll >= 4) k_diffcoef<4><<<flat_blocks((n2 + 3) / 4), 256, 0, st>>>(g, np, M, d, n2);
     else if (unroll >= 2) k_diffcoef<2><<<flat_blocks((n2 + 1) / 2), 256, 0, st>>>(g, np, M, d, n2);
     else k_diffcoef<1><<<flat_blocks(n2), 256, 0, st>>>(g, np, M, d, n2);
@@ -2775,9 +2777,14 @@ cudaError_t launch_xtail(double *x, const double *p, const DevScal *S, long long
 }
 
 cudaError_t launch_solvec(const SolveCArgs &a, cudaStream_t st) {
-    static const int unroll = getenv("PDEODE_SOLVEC_UNROLL") ? atoi(getenv("PDEODE_SOLVEC_UNROLL")) : 2;
-    if (unroll >= 2) k_solvec<2><<<flat_blocks((a.n2 + 1) / 2), 256, 0, st>>>(a);
-    else k_solvec<1><<<flat_blocks(a.n2), 256, 0, st>>>(a);
+    // The C update is bound by instruction issue (two IEEE divisions and a square root per
+    // cell: 65 % issue slots busy, fp64 pipe 39 %, profiles/r01_ncu_full_v3_production.md), not
+    // by loads in flight: the same sweep has one double2 per thread and 8 CTAs per SM at
+    // 0.180 ms, two at 0.196, 16 CTAs per SM at 0.186 / 0.207.
+    static const int unroll = getenv("PDEODE_SOLVEC_UNROLL") ? atoi(getenv("PDEODE_SOLVEC_UNROLL")) : 1;
+    static const int ctas = getenv("PDEODE_STREAM_CTAS") ? 0 : 8;     // 0: the global setting
+    if (unroll >= 2) k_solvec<2><<<flat_blocks((a.n2 + 1) / 2, ctas), 256, 0, st>>>(a);
+    else k_solvec<1><<<flat_blocks(a.n2, ctas), 256, 0, st>>>(a);
     return cudaGetLastError();
 }
 

@@ -89,6 +89,7 @@ def _lib():
         "pdeode_peak": [vp, dp, dp, dp],
         "pdeode_set_maxit": [vp, C.c_longlong],
         "pdeode_set_picard_cap": [vp, C.c_int],
+        "pdeode_reconfigure": [vp, C.POINTER(Params)],
         "pdeode_last_step_trace": [vp, llp, dp, C.c_int, ip],
         "pdeode_cg_trace_enable": [vp, C.c_int],
         "pdeode_cg_trace_get": [vp, dp, C.c_int, ip],
@@ -263,6 +264,11 @@ class Solver:
         a, b, c = C.c_double(peak), C.c_double(height), C.c_double(intfac)
         self._ck(self.lib.pdeode_peak(self.h, C.byref(a), C.byref(b), C.byref(c)), "peak")
         return a.value, b.value, c.value
+
+    def reconfigure(self, params):
+        """New parameters on the same grid (pdeode_reconfigure); set the state afterwards."""
+        self._ck(self.lib.pdeode_reconfigure(self.h, C.byref(params)), "reconfigure")
+        self.params = params
 
     def set_picard_cap(self, cap):
         self._ck(self.lib.pdeode_set_picard_cap(self.h, int(cap)), "set_picard_cap")

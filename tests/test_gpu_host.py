@@ -82,12 +82,18 @@ def test_ensemble_members_equal_single_runs(tmp_path):
     ge.build_cuda(); ge.build_host()
     files = []
     base = open(os.path.join(DATA, "square3d.txt")).read()
-    for k, h in enumerate((0.9, 0.8, 0.7, 0.6, 0.5), start=1):
-        txt = base.replace("height    = 0.9", f"height    = {h}")
+    # more members than worker threads, and every member with its own parameters: the threads'
+    # contexts are re-used from member to member (pdeode_reconfigure)
+    for k, h in enumerate((0.9, 0.8, 0.7, 0.6, 0.5, 0.85, 0.75), start=1):
+        txt = (base.replace("height    = 0.9", f"height    = {h}")
+               .replace("nu        = 0.30", f"nu        = {0.30 - 0.01 * k}")
+               .replace("delta     = 0.0001", f"delta     = {0.0001 * (1 + 0.1 * k)}")
+               .replace("beta      = 4", f"beta      = {3 + k % 3}"))
+        assert txt.count("0.30") == 0 and "delta     = 0.0001\n" not in txt
         (tmp_path / f"{k}.txt").write_text(txt)
         files.append(f"{k}.txt")
     exe = os.path.join(ge.BINDIR, "pdeode_ensemble")
-    env = dict(os.environ, PDEODE_SEED="1", PDEODE_MEMBERS_PER_GPU="3")
+    env = dict(os.environ, PDEODE_SEED="1", PDEODE_MEMBERS_PER_GPU="2", PDEODE_DEVICES="0")
     r = subprocess.run([exe] + files, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0, r.stdout + r.stderr
     solver = os.path.join(ge.BINDIR, "pdeode_solver")

@@ -459,3 +459,28 @@ def test_frames_decimated_on_device(pb, row, col, filt):
     assert np.array_equal(mm, want / col)
     assert mc == pytest.approx(C0.reshape(row, col)[::filt].mean(axis=1), rel=1e-14)
     s.close()
+
+
+@pytest.mark.parametrize("engine", ["kernels", "persistent", "whole-step"])
+def test_reconfigured_context_equals_a_fresh_one(pb, engine_env, engine):
+    """pdeode_reconfigure: new parameters on a used context give the bits a new context gives."""
+    engine_env(engine)
+    row, col = 70, 45
+    M0, C0 = ol.ic1(row, col, 0.8, 0.3)
+    p1 = pb.default_params(row)
+    p2 = pb.default_params(row, beta=5, nu=0.2, delta=2e-4, gama=0.7)
+    s = pb.Solver(row, col, p1)
+    s.set_state(M0, C0)
+    for _ in range(3):
+        s.step()
+    s.set_maxit(5); s.set_picard_cap(0)          # caps go back to their defaults as well
+    s.reconfigure(p2)
+    s.set_state(M0, C0)
+    f = pb.Solver(row, col, p2)
+    f.set_state(M0, C0)
+    for _ in range(3):
+        a, b = s.step_trace(), f.step_trace()
+        assert a["rc"] == b["rc"] == 0 and a["nits"] == b["nits"] and a["diffs"] == b["diffs"]
+    (Ma, Ca), (Mb, Cb) = s.get_state(), f.get_state()
+    assert np.array_equal(Ma, Mb) and np.array_equal(Ca, Cb)
+    s.close(); f.close()
