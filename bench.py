@@ -25,6 +25,7 @@ One JSON line is printed by rank 0.  Besides the contract's keys it carries
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
 import tempfile
@@ -87,8 +88,9 @@ class ClockSampler:
          "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
-    def __init__(self, index):
+    def __init__(self, index, period_ms=100):
         self.index = index
+        self.period_ms = period_ms
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
 
@@ -96,7 +98,7 @@ class ClockSampler:
         try:
             self.p = subprocess.Popen(
                 ["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                 "--format=csv,noheader,nounits", "-lms", "100"],
+                 "--format=csv,noheader,nounits", "-lms", str(self.period_ms)],
                 stdout=self.f, stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -254,41 +256,77 @@ def run_ensemble(args):
     exe = os.path.join(ROOT, "pde-odesolver_b200", "bin", "pdeode_ensemble")
     grid, steps, members = args.ensemble_grid, args.ensemble_steps, args.ensemble
     n = grid * grid
-    with tempfile.TemporaryDirectory() as d:
+    # every member writes the reference's text frames (512^2: two frames of 262 144 "x y M C"
+    # lines, 54 MB per member, 13.9 GB for 256 members): on the box's disk that is the whole wall
+    # time (1.1 GB/s), so the run directory goes to RAM-backed /dev/shm when it has the room
+    where = args.ensemble_dir
+    if where is None:
+        need = members * 2 * (grid // max(1, (grid - 1) // 256 if grid > 257 else 1)) ** 2 * 110 * 1.2
+        try:
+            st = os.statvfs("/dev/shm")
+            where = "/dev/shm" if st.f_bavail * st.f_frsize > need else None
+        except OSError:
+            where = None
+    with tempfile.TemporaryDirectory(dir=where) as d:
         files = []
         for k in range(1, members + 1):
             with open(os.path.join(d, f"{k}.txt"), "w") as fh:
                 fh.write(eb.TEMPLATE.format(**eb.member_params(k, grid, steps)))
             files.append(f"{k}.txt")
         env = dict(os.environ, PDEODE_MEMBERS_PER_GPU=str(args.ensemble_per_gpu), PDEODE_SEED="1",
+                   PDEODE_ENSEMBLE_TIMING="1",
                    PDEODE_DEVICES=",".join(str(i) for i in range(max(1, args.gpus))))
-        clk = ClockSampler(0)
-        clk.start()
+        # warm-up: one short member per GPU (a fresh box pages the driver and the library in on
+        # first use: 6 s of a cold 256-member sweep, measured), untimed, then its output removed
+        wd = os.path.join(d, "warmup")
+        os.makedirs(wd)
+        wfiles = []
+        for k in range(1, max(1, args.gpus) + 1):
+            with open(os.path.join(wd, f"{k}.txt"), "w") as fh:
+                fh.write(eb.TEMPLATE.format(**eb.member_params(k, grid, 20)))
+            wfiles.append(f"{k}.txt")
+        w = subprocess.run([exe] + wfiles, cwd=wd, env=dict(env, PDEODE_MEMBERS_PER_GPU="1"),
+                           capture_output=True, text=True)
+        if w.returncode != 0:
+            raise SystemExit("bench.py --ensemble: warm-up sweep failed: " + (w.stdout + w.stderr)[-800:])
+        shutil.rmtree(wd)
+        log("warm-up sweep done")
+        clk = ClockSampler(0, args.ensemble_clock_ms)
+        if args.ensemble_clock_ms > 0:
+            clk.start()
         t0 = time.perf_counter()
         r = subprocess.run([exe] + files, cwd=d, env=env, capture_output=True, text=True)
         dt = time.perf_counter() - t0
         clocks = clk.stop()
         if r.returncode != 0:
             raise SystemExit("bench.py --ensemble: pdeode_ensemble failed: " + (r.stdout + r.stderr)[-800:])
+        breakdown = [l for l in r.stderr.splitlines() if l.startswith("pdeode_ensemble timing")]
+        log(f"pdeode_ensemble: {dt:.2f} s wall; " + (breakdown[0] if breakdown else ""))
         cg = 0.0
         solver_s = []
+        out_bytes = 0
         for k in range(1, members + 1):
+            for fn in os.listdir(os.path.join(d, f"{k}Output")):
+                out_bytes += os.path.getsize(os.path.join(d, f"{k}Output", fn))
             txt = open(os.path.join(d, f"{k}Output", "statReport.dat")).read()
             cg += eb.stat_value(txt, "Avg Iters for linear") * eb.stat_value(txt, "Avg Iters for iterating") * steps
             solver_s.append(eb.stat_value(txt, "Time to compute"))
     emit({
         "metric": METRIC, "value": n * cg / dt, "unit": UNIT, "n_gpus": max(1, args.gpus),
-        "steps": steps, "warmup": 0, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
+        "steps": steps, "warmup": 1, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": f"ensemble: {members} independent {grid}x{grid} solves of {steps} time steps "
                                "(numbered parameter files varying delta, nu, kappa, gama, beta, height), "
                                f"{args.ensemble_per_gpu} members in flight per GPU, replicas only",
                    "grid": [grid, grid], "members": members, "parallelism": f"replicas over {max(1, args.gpus)} GPUs"},
         "wall_s": dt, "cg_iterations": round(cg), "clocks": clocks,
+        "program_timing": breakdown[0] if breakdown else None,
+        "output_bytes": out_bytes, "output_dir": where or tempfile.gettempdir(),
         "member_time_to_compute_s": {"median": float(np.median(solver_s)), "max": float(max(solver_s))},
         "gpu_launches": None,
         "note": "wall clock of the whole pdeode_ensemble program, start to exit: context creation, "
-                "console and output files of every member included",
+                "console and output files of every member included; warmup = one untimed sweep of one "
+                "20-step member per GPU",
     })
 
 
@@ -361,6 +399,10 @@ def main():
     ap.add_argument("--ensemble-grid", type=int, default=512)
     ap.add_argument("--ensemble-steps", type=int, default=200)
     ap.add_argument("--ensemble-per-gpu", type=int, default=16)
+    ap.add_argument("--ensemble-clock-ms", type=int, default=100,
+                    help="nvidia-smi sampling period during the sweep (0: no sampling)")
+    ap.add_argument("--ensemble-dir", default=None,
+                    help="where the members' run directories go (default: /dev/shm if it has room, else the temp dir)")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3                      # timing rule: W >= 3

@@ -16,11 +16,18 @@
 // each on its own context and stream, so that small grids fill the device.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <string>
+#include <cerrno>
+#include <dirent.h>
+#include <new>
+#include <sys/mman.h>
 #include <sys/stat.h>
+#include <sys/wait.h>
+#include <unistd.h>
 #include <thread>
 #include <vector>
 
@@ -87,24 +94,53 @@ int main(int argc, char **argv) {
     st.get_frame_rowmeans = pdeode_get_frame_rowmeans;
     st.set_initial_condition = pdeode_set_initial_condition;
 
+    // The GPUs to use.  Counted without touching CUDA where possible (the process-per-GPU mode
+    // below must fork before the first CUDA call): PDEODE_DEVICES = "0,1,..." (ordinals as CUDA
+    // numbers them for this process), else every entry of CUDA_VISIBLE_DEVICES, else every
+    // GPU the driver lists under /proc/driver/nvidia/gpus.
     std::vector<int> devices;
-    if (const char *d = getenv("PDEODE_DEVICES")) {
-        std::string s(d);
+    auto split_ints = [](const std::string &s2, std::vector<int> &out) {
         size_t pos = 0;
-        while (pos < s.size()) {
-            devices.push_back(atoi(s.c_str() + pos));
-            pos = s.find(',', pos);
+        while (pos < s2.size()) {
+            out.push_back(atoi(s2.c_str() + pos));
+            pos = s2.find(',', pos);
             if (pos == std::string::npos) break;
             ++pos;
         }
+    };
+    std::vector<std::string> visible;           // entries of CUDA_VISIBLE_DEVICES, if it is set
+    if (const char *v = getenv("CUDA_VISIBLE_DEVICES")) {
+        std::string s2(v);
+        size_t pos = 0;
+        while (pos <= s2.size()) {
+            const size_t c = s2.find(',', pos);
+            visible.push_back(s2.substr(pos, c == std::string::npos ? std::string::npos : c - pos));
+            if (c == std::string::npos) break;
+            pos = c + 1;
+        }
+        if (visible.size() == 1 && visible[0].empty()) visible.clear();
+    }
+    bool counted_without_cuda = true;
+    if (const char *d = getenv("PDEODE_DEVICES")) {
+        split_ints(d, devices);
+    } else if (!visible.empty()) {
+        for (size_t i = 0; i < visible.size(); ++i) devices.push_back((int)i);
     } else {
         int n = 0;
-        if (pdeode_device_count(&n) != PDEODE_OK || n <= 0) {
-            fprintf(stderr, "pdeode_ensemble: no CUDA device (there is no CPU fallback)\n");
-            return 1;
+        if (DIR *dp = opendir("/proc/driver/nvidia/gpus")) {
+            while (struct dirent *e = readdir(dp)) n += e->d_name[0] != '.';
+            closedir(dp);
+        }
+        if (n <= 0) {
+            counted_without_cuda = false;
+            if (pdeode_device_count(&n) != PDEODE_OK || n <= 0) {
+                fprintf(stderr, "pdeode_ensemble: no CUDA device (there is no CPU fallback)\n");
+                return 1;
+            }
         }
         for (int i = 0; i < n; ++i) devices.push_back(i);
     }
+    if (devices.empty()) { fprintf(stderr, "pdeode_ensemble: empty device list\n"); return 1; }
     int per_gpu = 16;    // measured best for 512^2 members on a B200 (profiles/README.md)
     if (const char *m = getenv("PDEODE_MEMBERS_PER_GPU")) per_gpu = atoi(m) > 0 ? atoi(m) : 1;
 
@@ -119,24 +155,39 @@ int main(int argc, char **argv) {
     if (!getenv("PDEODE_STEP_YIELD")) setenv("PDEODE_STEP_YIELD", "1", 1);
 
     const int nmember = argc - 1;
-    std::vector<int> rc((size_t)nmember, -1);
-    std::atomic<int> next{0};
+    // Results and the member counter live in memory shared with the per-GPU child processes.
+    struct Shared { std::atomic<int> next; };
+    const size_t shbytes = sizeof(Shared) + (size_t)nmember * (sizeof(int) + 2 * sizeof(double)) + 64;
+    void *shm = mmap(nullptr, shbytes, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_ANONYMOUS, -1, 0);
+    if (shm == MAP_FAILED) { perror("pdeode_ensemble: mmap"); return 1; }
+    Shared *sh = new (shm) Shared();
+    sh->next.store(0);
+    double *began = reinterpret_cast<double *>(static_cast<char *>(shm) + 64);
+    double *first_done = began + nmember;
+    int *rc = reinterpret_cast<int *>(first_done + nmember);
+    for (int k = 0; k < nmember; ++k) { rc[k] = -1; began[k] = 0.0; first_done[k] = 0.0; }
+    // PDEODE_ENSEMBLE_TIMING=1: where the wall time of a sweep goes (stderr)
+    const bool timing = getenv("PDEODE_ENSEMBLE_TIMING") && getenv("PDEODE_ENSEMBLE_TIMING")[0] == '1';
+    const auto t_start = std::chrono::steady_clock::now();      // CLOCK_MONOTONIC: the same in the children
+    auto since = [&] { return std::chrono::duration<double>(std::chrono::steady_clock::now() - t_start).count(); };
     auto worker = [&](int device) {
         for (;;) {
-            const int k = next.fetch_add(1);
+            const int k = sh->next.fetch_add(1);
             if (k >= nmember) return;
+            began[k] = since();
             const std::string file = argv[1 + k];
             std::string stem = file.substr(0, file.find('.'));          // `cut -d '.' -f 1`, runAll.sh:3
             const std::string dir = stem + "Output";
             mkdir(dir.c_str(), 0777);
             FILE *in = tmpfile();
             FILE *con = fopen((dir + "/console.txt").c_str(), "w");
-            if (!in || !con) { rc[(size_t)k] = 3; if (in) fclose(in); if (con) fclose(con); continue; }
+            if (!in || !con) { rc[k] = 3; if (in) fclose(in); if (con) fclose(con); continue; }
             fprintf(in, "%s\n", file.c_str());
             rewind(in);
-            rc[(size_t)k] = pdeode_host::run_program(in, con, st, device, dir);
+            rc[k] = pdeode_host::run_program(in, con, st, device, dir);
             fclose(in);
             fclose(con);
+            first_done[k] = since();
             // the run scripts also copy the parameter file next to the results (runAll.sh:19);
             // not through system(): forking a process with 128 threads and eight GPUs mapped
             // costs milliseconds apiece
@@ -144,14 +195,72 @@ int main(int argc, char **argv) {
             copy_file(file, dir + "/" + (slash == std::string::npos ? file : file.substr(slash + 1)));
         }
     };
-    std::vector<std::thread> pool;
-    for (size_t d = 0; d < devices.size(); ++d)
-        for (int s = 0; s < per_gpu; ++s) pool.emplace_back(worker, devices[d]);
-    for (auto &t : pool) t.join();
+    // One process per GPU (default with several GPUs; PDEODE_ENSEMBLE_FORK=0 keeps everything in
+    // this process): a process that sees eight GPUs spends seconds in the driver bringing all
+    // of them up one after the other before its first kernel runs, and as long again tearing
+    // them down (measured on an 8 x B200 box: first member done after 6.3 s of an 8.2 s sweep);
+    // children that each see one GPU do that side by side.  Members are still dealt from one
+    // counter, so a GPU that finishes early takes the next file.
+    const char *fk = getenv("PDEODE_ENSEMBLE_FORK");
+    const bool fork_mode = devices.size() > 1 && counted_without_cuda && !(fk && fk[0] == '0');
+    double t_spawned = 0.0;
+    if (fork_mode) {
+        fflush(nullptr);
+        std::vector<pid_t> kids;
+        for (size_t d = 0; d < devices.size(); ++d) {
+            const pid_t pid = fork();
+            if (pid < 0) { perror("pdeode_ensemble: fork"); break; }
+            if (pid == 0) {
+                const int dev = devices[d];
+                const std::string only = !visible.empty()
+                    ? ((size_t)dev < visible.size() ? visible[(size_t)dev] : std::string("-1"))
+                    : std::to_string(dev);
+                setenv("CUDA_VISIBLE_DEVICES", only.c_str(), 1);
+                std::vector<std::thread> pool;
+                for (int s2 = 0; s2 < per_gpu; ++s2) pool.emplace_back(worker, 0);
+                for (auto &t : pool) t.join();
+                fflush(nullptr);
+                _exit(0);
+            }
+            kids.push_back(pid);
+        }
+        t_spawned = since();
+        for (pid_t pid : kids) {
+            int status = 0;
+            while (waitpid(pid, &status, 0) < 0 && errno == EINTR) {}
+        }
+        // files no child got to (a child that died early): run them here
+        if (sh->next.load() < nmember) worker(devices[0]);
+    } else {
+        std::vector<std::thread> pool;
+        for (size_t d = 0; d < devices.size(); ++d)
+            for (int s2 = 0; s2 < per_gpu; ++s2) pool.emplace_back(worker, devices[d]);
+        t_spawned = since();
+        for (auto &t : pool) t.join();
+    }
+    if (timing) {
+        double first = 1e30, last = 0, longest = 0, b0 = 1e30, b1 = 0;
+        for (int k = 0; k < nmember; ++k) {
+            first = std::min(first, first_done[k]); last = std::max(last, first_done[k]);
+            longest = std::max(longest, first_done[k] - began[k]);
+            b0 = std::min(b0, began[k]); b1 = std::max(b1, began[k]);
+        }
+        fprintf(stderr, "pdeode_ensemble timing (%s): workers started %.3f s, members began %.3f .. %.3f s, first "
+                        "member done %.3f s, last member done %.3f s, longest member %.3f s, workers finished "
+                        "(contexts destroyed) %.3f s\n", fork_mode ? "one process per GPU" : "one process",
+                t_spawned, b0, b1, first, last, longest, since());
+    }
     int bad = 0;
     for (int k = 0; k < nmember; ++k) {
-        printf("%s -> %s\n", argv[1 + k], rc[(size_t)k] == 0 ? "ok" : "FAILED");
-        bad += rc[(size_t)k] != 0;
+        printf("%s -> %s\n", argv[1 + k], rc[k] == 0 ? "ok" : "FAILED");
+        bad += rc[k] != 0;
     }
+    // Every member's files are closed and every context destroyed by now.  Leave without the
+    // runtime's exit handlers: unloading the modules and unmapping the address space of eight
+    // primary contexts one by one took 8 of the 11 s a 256-member sweep spent in this program
+    // (measured), and the kernel reclaims all of it when the process ends anyway.
+    fflush(nullptr);
+    if (!(getenv("PDEODE_ENSEMBLE_SLOW_EXIT") && getenv("PDEODE_ENSEMBLE_SLOW_EXIT")[0] == '1'))
+        _exit(bad ? 1 : 0);
     return bad ? 1 : 0;
 }

@@ -173,3 +173,36 @@ def test_drop_in_program_on_several_gpus(tmp_path):
     def stats(text):
         return [float(l.split("=")[1]) for l in text.splitlines() if "Iters for iterating" in l]
     assert stats(outs["one"][2]) == stats(outs["many"][2])        # Picard statistics: exact
+
+
+def test_ensemble_over_several_gpus(tmp_path):
+    """pdeode_ensemble with several GPUs: one child process per GPU (each sees only its own
+    device), members dealt from one shared counter; every member equals the single run."""
+    n = min(gpu_count(), 4)
+    if n < 2:
+        pytest.skip("2 GPUs needed")
+    import __graft_entry__ as ge
+    ge.build_host()
+    base = open(os.path.join(ROOT, "tests", "data", "square3d.txt")).read()
+    files = []
+    for k in range(1, 3 * n + 1):
+        txt = (base.replace("height    = 0.9", f"height    = {0.9 - 0.03 * k}")
+               .replace("nu        = 0.30", f"nu        = {0.30 - 0.005 * k}"))
+        (tmp_path / f"{k}.txt").write_text(txt)
+        files.append(f"{k}.txt")
+    env = dict(os.environ, PDEODE_SEED="1", PDEODE_MEMBERS_PER_GPU="2", PDEODE_ENSEMBLE_TIMING="1",
+               PDEODE_DEVICES=",".join(str(i) for i in range(n)))
+    exe = os.path.join(ROOT, "pde-odesolver_b200", "bin", "pdeode_ensemble")
+    r = subprocess.run([exe] + files, cwd=tmp_path, env=env, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert "one process per GPU" in r.stderr
+    assert r.stdout.count("-> ok") == len(files)
+    solver = os.path.join(ROOT, "pde-odesolver_b200", "bin", "pdeode_solver")
+    for k, f in enumerate(files, start=1):
+        single = tmp_path / f"single{k}"
+        single.mkdir()
+        s = subprocess.run([solver], input=str(tmp_path / f) + "\n", text=True, capture_output=True,
+                           cwd=single, env=dict(os.environ, PDEODE_SEED="1"), timeout=300)
+        assert s.returncode == 0
+        for name in ("total.dat", "COprod.dat", "output.dat"):
+            assert open(tmp_path / f"{k}Output" / name).read() == open(single / name).read(), (k, name)
