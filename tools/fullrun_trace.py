@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--frame-every", type=int, default=333)   # filter = int(tEnd/(nOuts*tDel)) (P:638)
     ap.add_argument("--stride", type=int, default=0)          # 0: 2 for <= 512, else 8
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--omp", type=int, default=0,
+                    help="oracle only: the OpenMP build (the reference's runAll_paral.sh variant) on "
+                         "this many threads instead of the serial build")
     ap.add_argument("--out", required=True)
     ap.add_argument("--checkpoint", action="store_true",
                     help="write <out>.ckpt.npz (trace so far + full state) at every frame and "
@@ -43,8 +46,13 @@ def main():
     M0, C0 = ol.ic_blobs(row, col, 0.02, 0.0390625, 60, args.seed)   # MinitialCond = 5, fixed seed (D5)
     if args.impl == "oracle":
         ol.build_oracle()
-        s = ol.Oracle(row, col, ol.default_params(row))
-        info = "serial CPU oracle (bit-identical to the reference's translated source)"
+        if args.omp > 0:
+            os.environ["OMP_NUM_THREADS"] = str(args.omp)
+            s = ol.Oracle(row, col, ol.default_params(row), omp=True)
+            info = f"OpenMP CPU oracle on {args.omp} threads (the reference's runAll_paral.sh build, restated)"
+        else:
+            s = ol.Oracle(row, col, ol.default_params(row))
+            info = "serial CPU oracle (bit-identical to the reference's translated source)"
     else:
         import pdeode_b200 as pb
         s = pb.Solver(row, col, pb.default_params(row))
