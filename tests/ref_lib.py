@@ -30,7 +30,12 @@ def build():
 
 
 def program(omp=False):
+    """The reference program: the real gfortran build of runAll.sh:6 where oracle/Makefile could
+    make one (a box with a gfortran), else the translated build."""
     build()
+    real = os.path.join(REF_DIR, "ref_omp_gfortran" if omp else "ref_serial_gfortran")
+    if os.path.exists(real) and os.environ.get("PDEODE_REF_TRANSLATED") != "1":
+        return real
     return os.path.join(REF_DIR, "ref_omp" if omp else "ref_serial")
 
 
