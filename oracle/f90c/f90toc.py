@@ -31,6 +31,13 @@ Language rules implemented (gfortran -O3 -fdefault-real-8 semantics):
     pages are in practice.
   * !$omp directives become #pragma omp (only compiled in with -fopenmp).
   * I/O, system_clock, random_seed / random_number go to a small runtime (f90rt.c).
+  * ISO_C_BINDING (for a host that keeps its Fortran and calls a C library): a module made
+    of `parameter` constants, bind(C) derived types and an interface block of bind(C)
+    functions is read, not translated -- its functions become C prototypes by the
+    interoperability rules (a VALUE dummy by value, every other dummy a pointer to the
+    interoperable type; type(c_ptr) = void *; a bind(C) type = the struct with the same
+    components in order); `use` of it makes the names visible; kinds c_int, c_long_long,
+    c_double; structure constructors become compound literals; iand() is `&`.
 
 Usage: f90toc.py -o out.c file1.f90 file2.f90 ...
 """
@@ -411,15 +418,114 @@ class Unit:
         self.body = []            # (kind, text, lineno)
 
 
-CTYPE = {'int': 'int', 'real': 'double', 'char': 'char'}
+class _CType(dict):
+    def __missing__(self, key):              # 'struct:name' -> the bind(C) type
+        if key.startswith('struct:'):
+            return 'struct ' + key[7:]
+        raise KeyError(key)
+
+
+CTYPE = _CType({'int': 'int', 'real': 'double', 'char': 'char', 'i64': 'long long', 'cptr': 'void *'})
+KINDS = {('integer', 'c_int'): 'int', ('integer', 'c_long_long'): 'i64', ('real', 'c_double'): 'real',
+         ('type', 'c_ptr'): 'cptr'}
+
+
+def kind_type(base, sel):
+    """integer(c_int) / real(c_double) / type(c_ptr) / type(name) -> type key."""
+    sel = sel.strip().lower()
+    sel = re.sub(r'^kind\s*=\s*', '', sel)
+    if (base, sel) in KINDS:
+        return KINDS[(base, sel)]
+    if base == 'type':
+        return 'struct:' + sel
+    raise SyntaxError(f"unsupported kind {base}({sel})")
+
+
+class Module:
+    """A module of constants, bind(C) types and bind(C) function interfaces (see the header)."""
+    def __init__(self, name, path):
+        self.name, self.path = name, path
+        self.consts = {}          # name -> (type, value text)
+        self.types = {}           # name -> [(type, component)]
+        self.funcs = {}           # fortran name -> (C name, result type, [(dummy, type, by_value, is_array, intent)])
+
+
+def parse_module(name, body, path):
+    m = Module(name, path)
+    k = 0
+    while k < len(body):
+        kind, text, ln = body[k]
+        low = text.lower()
+        k += 1
+        if re.match(r'(use\s|implicit\s+none\b|interface\b|end\s*interface\b|contains\b)', low):
+            continue
+        mt = re.match(r'type\s*,\s*bind\s*\(\s*c\s*\)\s*::\s*(\w+)$', low)
+        if mt:
+            comps = []
+            while not re.match(r'end\s*type\b', body[k][1].lower()):
+                d = DECL.match(body[k][1])
+                base, rest = d.group(1).lower(), d.group(2).strip()
+                e = match_paren(rest, 0)
+                t = kind_type(base, rest[1:e])
+                ents = rest[e + 1:].split('::', 1)[1]
+                for ent in split_top(ents, ','):
+                    comps.append((t, ent.split('=')[0].strip()))
+                k += 1
+            k += 1
+            m.types[mt.group(1)] = comps
+            continue
+        mp = re.match(r'(integer|real)\s*\(\s*(\w+)\s*\)\s*,\s*parameter\s*::\s*(\w+)\s*=\s*(.+)$', text, re.I)
+        if mp:
+            m.consts[mp.group(3).lower()] = (kind_type(mp.group(1).lower(), mp.group(2)), mp.group(4).strip())
+            continue
+        mf = re.match(r'(integer|real)\s*\(\s*(\w+)\s*\)\s*function\s+(\w+)\s*\((.*?)\)\s*'
+                      r'bind\s*\(\s*c\s*,\s*name\s*=\s*["\'](\w+)["\']\s*\)$', text, re.I)
+        if mf:
+            ret = kind_type(mf.group(1).lower(), mf.group(2))
+            dummies = [a.strip().lower() for a in mf.group(4).split(',') if a.strip()]
+            decl = {}
+            while not re.match(r'end\s*function\b', body[k][1].lower()):
+                t2 = body[k][1]
+                k += 1
+                if re.match(r'import\b', t2, re.I):
+                    continue
+                d = DECL.match(t2)
+                base, rest = d.group(1).lower(), d.group(2).strip()
+                e = match_paren(rest, 0)
+                t = kind_type(base, rest[1:e])
+                attrs, ents = rest[e + 1:].split('::', 1)
+                attrs = [a.lower().replace(' ', '') for a in split_top(attrs.strip().lstrip(','), ',') if a]
+                intent = next((a[7:-1] for a in attrs if a.startswith('intent(')), None)
+                for ent in split_top(ents, ','):
+                    decl[ent.strip().lower()] = (t, 'value' in attrs, any(a.startswith('dimension(') for a in attrs), intent)
+            k += 1
+            m.funcs[mf.group(3).lower()] = (mf.group(5), ret, [(a,) + decl[a] for a in dummies])
+            continue
+        raise SyntaxError(f"{path}:{ln}: unsupported statement in module {name}: {text}")
+    return m
+
+
 INTRINSICS = {'abs', 'sqrt', 'real', 'int', 'mod', 'max0', 'min0', 'max', 'min', 'sum', 'maxval',
               'len'}
 
 
 def parse_units(stmts, path):
     units, cur, in_iface = [], None, False
+    mod_name, mod_body = None, []
     for kind, text, ln in stmts:
         low = text.lower()
+        if kind == 'stmt' and cur is None:
+            mm = re.match(r'module\s+(\w+)\s*$', low)
+            if mm and mod_name is None:
+                mod_name, mod_body = mm.group(1), []
+                continue
+            if mod_name is not None:
+                if re.match(r'end\s*module\b', low):
+                    units.append(parse_module(mod_name, mod_body, path))
+                    mod_name = None
+                else:
+                    mod_body.append((kind, text, ln))
+                continue
         if kind == 'stmt':
             if re.match(r'interface\b', low):
                 in_iface = True
@@ -451,7 +557,7 @@ def parse_units(stmts, path):
     return units
 
 
-DECL = re.compile(r'^(integer|real|character)\b(.*)$', re.I)
+DECL = re.compile(r'^(integer|real|character|type)\b(.*)$', re.I)
 
 
 def parse_decl(u, text):
@@ -462,6 +568,13 @@ def parse_decl(u, text):
     base = m.group(1).lower()
     rest = m.group(2).strip()
     charlen = None
+    ktype = None
+    if base == 'type' and not rest.startswith('('):
+        return False                      # `type, bind(C) :: name` is a module matter
+    if base in ('integer', 'real', 'type') and rest.startswith('('):
+        e = match_paren(rest, 0)
+        ktype = kind_type(base, rest[1:e])
+        rest = rest[e + 1:].strip()
     if base == 'character':
         charlen = '1'
         if rest.startswith('('):
@@ -494,7 +607,7 @@ def parse_decl(u, text):
             raise SyntaxError(f"cannot parse entity {ent!r} in {text!r}")
         name = m2.group(1).lower()
         s = u.syms.setdefault(name, Sym(name))
-        s.type = {'integer': 'int', 'real': 'real', 'character': 'char'}[base]
+        s.type = ktype or {'integer': 'int', 'real': 'real', 'character': 'char'}[base]
         s.dims = split_top(m2.group(2), ',') if m2.group(2) else dims
         s.intent = intent
         s.allocatable = alloc
@@ -506,7 +619,8 @@ def parse_decl(u, text):
 
 class Gen:
     def __init__(self, units):
-        self.units = {u.name: u for u in units}
+        self.modules = {u.name: u for u in units if isinstance(u, Module)}
+        self.units = {u.name: u for u in units if not isinstance(u, Module)}
         self.out = []
         self.u = None
         self.ind = 1
@@ -518,6 +632,14 @@ class Gen:
     # ---- names
     def v(self, name):
         return name + '_'
+
+    def used(self, what, name):
+        """(module entity) the current unit sees through `use`: what = consts | types | funcs."""
+        for mn in getattr(self.u, 'uses', ()):
+            d = getattr(self.modules[mn], what)
+            if name in d:
+                return d[name]
+        return None
 
     def sym(self, name):
         s = self.u.syms.get(name)
@@ -550,7 +672,7 @@ class Gen:
             if e.op in ('&&', '||') or getattr(e, 'rel', False):
                 return 'int'
             ta, tb = self.typeof(e.a), self.typeof(e.b)
-            return 'real' if 'real' in (ta, tb) else 'int'
+            return 'real' if 'real' in (ta, tb) else ('i64' if 'i64' in (ta, tb) else 'int')
         if k == 'pow':
             return self.typeof(e.a)
         if k == 'cons':
@@ -559,6 +681,14 @@ class Gen:
         if k == 'ref':
             if e.name in self.u.syms:
                 return self.sym(e.name).type
+            if self.used('consts', e.name):
+                return self.used('consts', e.name)[0]
+            if self.used('funcs', e.name):
+                return self.used('funcs', e.name)[1]
+            if self.used('types', e.name):
+                return 'struct:' + e.name
+            if e.name == 'iand':
+                return 'int'
             if e.name in ('real', 'sqrt'):
                 return 'real'
             if e.name in ('int', 'mod', 'max0', 'min0', 'len'):
@@ -657,6 +787,20 @@ class Gen:
                 raise SyntaxError(f"{self.u.name}: {name} is not an array")
             return self.v(name)
         a = e.args or []
+        if self.used('consts', name):
+            return '(' + self.used('consts', name)[1] + ')'
+        if self.used('funcs', name):
+            cname, _, dummies = self.used('funcs', name)
+            if len(a) != len(dummies):
+                raise SyntaxError(f"{self.u.name}: {name} takes {len(dummies)} arguments")
+            return f"{cname}({', '.join(self.cx(x) if d[2] else self.actual(x) for x, d in zip(a, dummies))})"
+        if self.used('types', name):                  # structure constructor, components in order
+            comps = self.used('types', name)
+            if len(a) != len(comps):
+                raise SyntaxError(f"{self.u.name}: {name}(...) needs {len(comps)} components")
+            return f"((struct {name}){{{', '.join(self.cx(x) for x in a)}}})"
+        if name == 'iand':
+            return f"(({self.cx(a[0], idx)}) & ({self.cx(a[1], idx)}))"
         if name == 'abs':
             f = 'fabs' if self.typeof(a[0]) == 'real' else 'abs'
             return f"{f}({self.cx(a[0], idx)})"
@@ -1014,8 +1158,12 @@ class Gen:
         self.pending_pragma = None
         # declarations first
         body = []
+        u.uses = []
         for kind, text, ln in u.body:
             if kind == 'stmt':
+                mu = re.match(r'use\s+(\w+)', text, re.I)
+                if mu and mu.group(1).lower() in self.modules:
+                    u.uses.append(mu.group(1).lower())
                 if re.match(r'implicit\s+none\b', text, re.I) or re.match(r'use\s', text, re.I):
                     continue
                 if parse_decl(u, text):
@@ -1035,7 +1183,9 @@ class Gen:
         # locals: scalars first (array extents may use them ... only dummies in practice)
         locs = [s for s in u.syms.values() if not s.dummy]
         for s in locs:
-            if s.dims is None and s.type != 'char':
+            if s.dims is None and s.type.startswith('struct:'):
+                self.emit(f"{CTYPE[s.type]} {self.v(s.name)} = {{0}};")
+            elif s.dims is None and s.type != 'char':
                 self.emit(f"{CTYPE[s.type]} {self.v(s.name)} = 0;")
             elif s.dims is None:
                 n = self.cx(parse_expr(s.charlen))
@@ -1078,6 +1228,16 @@ class Gen:
                 if kind == 'stmt':
                     parse_decl(u, text)
         protos = []
+        for mod in self.modules.values():
+            protos.append(f"/* module {mod.name}: {mod.path} (interoperability rules) */")
+            for tn, comps in mod.types.items():
+                protos.append(f"struct {tn} {{ " + ' '.join(f"{CTYPE[t]} {c};" for t, c in comps) + " };")
+            for cname, ret, dummies in mod.funcs.values():
+                ps = []
+                for _, t, by_value, _, intent in dummies:
+                    ct = CTYPE[t]
+                    ps.append(ct if by_value else (("const " if intent == 'in' else "") + ct + " *"))
+                protos.append(f"extern {CTYPE[ret]} {cname}({', '.join(ps) if ps else 'void'});")
         for u in self.units.values():
             self.u = u
             protos.append(self.signature(u) + ';')

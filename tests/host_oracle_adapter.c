@@ -106,3 +106,17 @@ static const stepper_table TABLE = {a_create, a_set_state, a_get_state, a_step,
                                     0};
 
 const void *oracle_stepper_table(void) { return &TABLE; }
+
+#ifdef ADAPTER_EXPORT_ABI
+/* The same functions under the C ABI's own names, so that a host program LINKED against
+ * libpdeode_b200.so's interface (the reference's Fortran host patched by
+ * pde-odesolver_b200/fortran/patch_reference.py, tests/test_fortran_host.py) can be run on a
+ * machine without a GPU.  A separate test-only library; never loaded next to the real one. */
+int pdeode_create(pdeode_ctx **c, int row, int col, const pdeode_params *p, int dev) { return a_create(c, row, col, p, dev); }
+int pdeode_set_state(pdeode_ctx *c, const double *M, const double *C) { return a_set_state(c, M, C); }
+int pdeode_get_state(pdeode_ctx *c, double *M, double *C) { return a_get_state(c, M, C); }
+int pdeode_step(pdeode_ctx *c, int *cnt, long long *sum, long long *mx) { return a_step(c, cnt, sum, mx); }
+int pdeode_mass(pdeode_ctx *c, double *mM, double *mC) { return a_mass(c, mM, mC); }
+int pdeode_peak(pdeode_ctx *c, double *peak, double *height, double *intfac) { return a_peak(c, peak, height, intfac); }
+int pdeode_destroy(pdeode_ctx *c) { return a_destroy(c); }
+#endif
