@@ -13,8 +13,8 @@ and output files stay the reference's own code.  Build (a machine with a Fortran
     gfortran -O3 -fdefault-real-8 pdeode_b200_mod.f90 PDE-ODEsolver_b200.f90 init_random_seed.f90 \\
              -L$REPO/pde-odesolver_b200/lib -lpdeode_b200 -Wl,-rpath,$REPO/pde-odesolver_b200/lib
 
-(CGdiag.f90 is no longer needed.)  In this image, which has no Fortran compiler, the same two files go
-through oracle/f90c/f90toc.py (tests/test_fortran_host.py).
+(CGdiag.f90 is no longer needed.)  This image has no Fortran compiler; how the same two files are
+built and run here nevertheless: tests/test_fortran_host.py.
 
 The edits are anchored on statements of solveOrder2 (PDE-ODEsolver.f90:600-763); an anchor that is
 missing or ambiguous means the source is not the one this was written for, and nothing is written.
