@@ -97,3 +97,84 @@ def test_fortran_host_on_the_gpu(tmp_path, pfile):
         a = np.array([float(t) for t in (tmp_path / "tree" / f).read_text().split()])
         b = np.array([float(t) for t in (tmp_path / "cxx" / f).read_text().split()])
         assert a.shape == b.shape and np.allclose(a, b, rtol=1e-9, atol=1e-13), f
+
+
+def test_translator_iso_c_binding_rules(tmp_path):
+    """The translator's ISO_C_BINDING rules on a probe: VALUE dummies by value, the others by
+    address, type(c_ptr) in and out, a bind(C) type's constructor in component order,
+    c_long_long results in real arithmetic, module parameters, iand."""
+    import ctypes as C
+    import sys
+    (tmp_path / "m.f90").write_text("""
+module probe_c
+    use iso_c_binding
+    implicit none
+    integer(c_int), parameter :: PROBE_MASK = 255
+    type, bind(C) :: pair
+        real(c_double) :: a
+        integer(c_int) :: k, pad = 0
+    end type pair
+    interface
+        integer(c_int) function probe_open(h, p, scale) bind(C, name="probe_open")
+            import :: c_ptr, c_int, c_double, pair
+            type(c_ptr), intent(out) :: h
+            type(pair), intent(in) :: p
+            real(c_double), value :: scale
+        end function
+        integer(c_int) function probe_run(h, n, x, total, big) bind(C, name="probe_run")
+            import :: c_ptr, c_int, c_double, c_long_long
+            type(c_ptr), value :: h
+            integer(c_int), value :: n
+            real(c_double), dimension(*), intent(inout) :: x
+            real(c_double), intent(out) :: total
+            integer(c_long_long), intent(out) :: big
+        end function
+    end interface
+end module probe_c
+""")
+    (tmp_path / "s.f90").write_text("""
+subroutine drive(n, x, out)
+    use probe_c
+    implicit none
+    integer, intent(in) :: n
+    real, dimension(n), intent(inout) :: x
+    real, dimension(4), intent(out) :: out
+    type(c_ptr) :: h
+    type(pair) :: p
+    integer(c_int) :: rc
+    integer(c_long_long) :: big
+    real :: total, acc
+    p = pair(1.5, n, 0)
+    rc = probe_open(h, p, 2.0)
+    out(1) = rc
+    rc = probe_run(h, n, x, total, big)
+    out(2) = total
+    acc = 0.5
+    acc = acc + big
+    out(3) = acc
+    out(4) = iand(rc, PROBE_MASK)
+end subroutine
+""")
+    (tmp_path / "c.c").write_text("""
+#include <stdlib.h>
+struct pair { double a; int k, pad; };
+struct st { double a, scale; int k; };
+int probe_open(void **h, const struct pair *p, double scale) {
+    struct st *s = malloc(sizeof *s); s->a = p->a; s->k = p->k; s->scale = scale; *h = s; return 7; }
+int probe_run(void *h, int n, double *x, double *total, long long *big) {
+    struct st *s = h; double t = 0; for (int i = 0; i < n; ++i) { x[i] = x[i] * s->scale + s->a; t = t + x[i]; }
+    *total = t; *big = 5000000000LL + s->k; free(s); return 0x1234; }
+""")
+    gen = tmp_path / "gen.c"
+    f90c = os.path.join(fh.ROOT, "oracle", "f90c")
+    subprocess.check_call([sys.executable, os.path.join(f90c, "f90toc.py"), "-o", str(gen),
+                           str(tmp_path / "m.f90"), str(tmp_path / "s.f90")])
+    so = tmp_path / "probe.so"
+    subprocess.check_call(["/usr/bin/gcc", "-O2", "-std=gnu11", "-fPIC", "-shared", "-I" + f90c, "-o", str(so), str(gen),
+                           str(tmp_path / "c.c"), os.path.join(f90c, "f90rt.c"), "-lm"])
+    lib = C.CDLL(str(so))
+    x = np.array([1.0, 2.0, 3.0])
+    out = np.zeros(4)
+    lib.drive_(C.byref(C.c_int(3)), x.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+    assert list(x) == [3.5, 5.5, 7.5]
+    assert list(out) == [7.0, 16.5, 5000000003.5, float(0x34)]
