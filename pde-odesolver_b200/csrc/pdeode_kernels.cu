@@ -2664,8 +2664,9 @@ int stencil_max_blocks(const GridDesc &g, int TR) {
 cudaError_t launch_diffcoef(const GridDesc &g, const NumParams &np, const double *M, double *d,
                             cudaStream_t st) {
     const long long n2 = (long long)g.rows * g.P / 2;
-    // sweep at 4096^2 (profiles/r02_sweep_pointwise.jsonl): 0.104 ms with one or two double2 per
-    // thread in flight, 0.112 with four; 0.093 once the integer powers are unrolled (powi_fast)
+    // sweep at 4096^2 (tools/sweep_pointwise.sh): 0.104 ms with one or two double2 per thread in
+    // flight, 0.112 with four; 0.093 once the integer powers are unrolled (powi_fast); the default
+    // re-timed on the final code: 0.082 ms (profiles/r02_kernel_times_4096.jsonl)
     static const int unroll = getenv("PDEODE_DIFFCOEF_UNROLL") ? atoi(getenv("PDEODE_DIFFCOEF_UNROLL")) : 2;
     if (unroll >= 4) k_diffcoef<4><<<flat_blocks((n2 + 3) / 4), 256, 0, st>>>(g, np, M, d, n2);
     else if (unroll >= 2) k_diffcoef<2><<<flat_blocks((n2 + 1) / 2), 256, 0, st>>>(g, np, M, d, n2);
