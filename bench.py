@@ -83,16 +83,25 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """nvidia-smi clocks / throttle reasons during the timed region.
+
+    start() is called BEFORE the warm-up steps and begin() right before the timed region: the
+    sampler's own start-up (process spawn, NVML attaching to every GPU of the box: some hundred
+    milliseconds during which launches and context operations stall -- it doubled the wall time
+    of the ensemble sweep, see clock_snapshot) then falls into the warm-up, and only the samples
+    stamped inside [begin, stop] are reported."""
+    FIELDS = ("timestamp", "index", "clocks.sm", "clocks.max.sm", "power.draw", "clocks_event_reasons.active",
+              "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
+              "clocks_event_reasons.sw_thermal_slowdown", "clocks_event_reasons.sw_power_cap")
+    Q = ",".join(FIELDS)
+    REASONS = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
 
     def __init__(self, index, period_ms=100):
         self.index = index
         self.period_ms = period_ms
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         self.p = None
+        self.t_begin = None
 
     def start(self):
         try:
@@ -103,7 +112,30 @@ class ClockSampler:
         except Exception:
             self.p = None
 
+    def begin(self):
+        self.t_begin = time.time()
+
+    @staticmethod
+    def parse_line(line):
+        """-> (unix time or None, sm MHz, max sm MHz, [reasons]) or None for a line that is not a sample."""
+        c = [t.strip() for t in line.split(",")]
+        if len(c) < len(ClockSampler.FIELDS):
+            return None
+        try:
+            sm, mx = float(c[2]), float(c[3])
+        except ValueError:
+            return None
+        ts = None
+        try:                                     # "2026/10/20 13:22:01.123", local time
+            head, _, ms = c[0].partition(".")
+            ts = time.mktime(time.strptime(head, "%Y/%m/%d %H:%M:%S")) + (float("0." + ms) if ms.isdigit() else 0.0)
+        except (ValueError, OverflowError):
+            ts = None
+        reasons = [n for n, v in zip(ClockSampler.REASONS, c[6:10]) if v.lower().startswith("active")]
+        return ts, sm, mx, reasons
+
     def stop(self):
+        t_end = time.time()
         if self.p is not None:
             self.p.terminate()
             try:
@@ -112,41 +144,33 @@ class ClockSampler:
                 self.p.kill()
         self.f.flush()
         self.f.seek(0)
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.f:
-            c = [t.strip() for t in line.split(",")]
-            if len(c) < 9:
-                continue
-            try:
-                sm.append(float(c[1])); mx.append(float(c[2]))
-            except ValueError:
-                continue
-            for nme, v in zip(names, c[5:9]):
-                if v.lower().startswith("active"):
-                    reasons.add(nme)
+        rows = [r for r in (self.parse_line(l) for l in self.f) if r is not None]
         self.f.close()
         try:
             os.unlink(self.f.name)
         except OSError:
             pass
-        if not sm:
+        window = "all samples since the sampler started"
+        if self.t_begin is not None:
+            slack = 1e-3 * self.period_ms
+            inside = [r for r in rows if r[0] is not None and self.t_begin - slack <= r[0] <= t_end + slack]
+            if inside:
+                rows, window = inside, "samples stamped inside the timed region (sampler started before the warm-up)"
+        if not rows:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)),
-                "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median([r[1] for r in rows])), "sm_max_mhz": float(max(r[2] for r in rows)),
+                "reasons": sorted({n for r in rows for n in r[3]}), "samples": len(rows), "window": window}
 
 
 def clock_snapshot(index):
     """One nvidia-smi query (clocks, throttle reasons) -- for runs a sampler would disturb."""
-    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
     out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0,
            "when": "one query right after the sweep (no sampler during it)"}
     try:
         txt = subprocess.run(["nvidia-smi", "-i", str(index), f"--query-gpu={ClockSampler.Q}",
                               "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=30).stdout
-        c = [t.strip() for t in txt.strip().splitlines()[0].split(",")]
-        out["sm_mhz"], out["sm_max_mhz"], out["samples"] = float(c[1]), float(c[2]), 1
-        out["reasons"] = sorted(n for n, v in zip(names, c[5:9]) if v.lower().startswith("active"))
+        r = ClockSampler.parse_line(txt.strip().splitlines()[0])
+        out["sm_mhz"], out["sm_max_mhz"], out["samples"], out["reasons"] = r[1], r[2], 1, sorted(r[3])
     except Exception:
         pass
     return out
@@ -514,15 +538,17 @@ def main():
         pic_total[0] += r["countIters"]
         return r["nitSum"]
 
+    clk = ClockSampler(local)
+    if rank == 0:
+        clk.start()                          # its start-up falls into the warm-up
     it_warm = 0
     for _ in range(args.warmup):
         it_warm += resident_step()
     l0 = s.launch_count()
-    clk = ClockSampler(local)
-    if rank == 0:
-        clk.start()
+    clk.begin()
     t_res, it_res = timed(resident_step, args.steps)
-    clocks = clk.stop() if rank == 0 else None
+    clocks = clk.stop()
+    clocks = clocks if rank == 0 else None
     launches = s.launch_count() - l0
     value = n * it_res / t_res
     if rank == 0:
@@ -685,13 +711,15 @@ def main():
                     s16.set_initial_condition(1, args.depth, height)
                 return s16.step()["nitSum"]
 
-            for _ in range(w16):
-                step16()
             clk16 = ClockSampler(local)
             if rank == 0:
                 clk16.start()
+            for _ in range(w16):
+                step16()
+            clk16.begin()
             t16, it16 = timed(step16, k16)
-            c16 = clk16.stop() if rank == 0 else None
+            c16 = clk16.stop()
+            c16 = c16 if rank == 0 else None
             mM, mC = s16.mass()
             strong[name] = {"value": n16 * it16 / t16, "ms_per_step": 1e3 * t16 / k16, "steps": k16,
                             "warmup": w16, "cg_iterations": it16, "clocks": c16,
