@@ -65,7 +65,7 @@ def test_sampler_reports_only_the_timed_window(bench, fake_smi):
     time.sleep(0.5)
     r = c.stop()
     assert r["sm_mhz"] == 1965.0 and r["sm_max_mhz"] == 1980.0 and r["reasons"] == ["sw_power_cap"]
-    assert 5 <= r["samples"] <= 13, r          # ~0.5 s / 50 ms, not the ~1.1 s since the start
+    assert 2 <= r["samples"] <= 14, r          # ~0.5 s / 50 ms (fewer on a loaded box), not the ~1.1 s since the start (>= 16)
     assert "inside the timed region" in r["window"]
 
 
