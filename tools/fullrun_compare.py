@@ -14,16 +14,26 @@ def main():
     ap.add_argument("ref")
     ap.add_argument("other")
     ap.add_argument("--label", default="")
+    ap.add_argument("--steps", type=int, default=0,
+                    help="compare the first N steps only (a run still under way: its <out>.ckpt.npz)")
     a = ap.parse_args()
     r = np.load(a.ref, allow_pickle=True)
     o = np.load(a.other, allow_pickle=True)
     n = min(len(r["count"]), len(o["count"]))
+    if "k" in r.files:                       # a checkpoint: steps done so far
+        n = min(n, int(r["k"]))
+    if "k" in o.files:
+        n = min(n, int(o["k"]))
+    if a.steps > 0:
+        n = min(n, a.steps)
+    nfr = min(len(r["frames_at"]), len(o["frames_at"]),
+              int((np.asarray(r["frames_at"]) <= n).sum()), int((np.asarray(o["frames_at"]) <= n).sum()))
     grid = int(r["grid"])
     print(f"### {a.label or (a.other + ' vs ' + a.ref)}")
-    print(f"grid {grid} x {grid}, {n} time steps, {len(r['frames_at'])} frames; "
+    print(f"grid {grid} x {grid}, {n} time steps, {nfr} frames; "
           f"reference side: {str(r['info'])}; other side: {str(o['info'])}\n")
     same_frames = [(str(x) == str(y)) and (str(u) == str(v))
-                   for x, y, u, v in zip(r["hashM"], o["hashM"], r["hashC"], o["hashC"])]
+                   for x, y, u, v in zip(r["hashM"][:nfr], o["hashM"][:nfr], r["hashC"][:nfr], o["hashC"][:nfr])]
     print(f"* frames bit-identical (sha256 of M and of C): **{sum(same_frames)} of {len(same_frames)}**"
           + ("" if all(same_frames) else f" (first difference at frame {same_frames.index(False)}, "
                                           f"step {int(r['frames_at'][same_frames.index(False)])})"))
@@ -45,8 +55,8 @@ def main():
           f"max CG per solve {int(r['nitmax'][:n].max())} vs {int(o['nitmax'][:n].max())}")
     first = int(np.argmax(dn != 0)) if (dn != 0).any() else -1
     print(f"* first step whose CG count differs: {first if first >= 0 else 'none'}")
-    eM = [float(np.linalg.norm(x - y) / max(np.linalg.norm(x), 1e-300)) for x, y in zip(r["M"], o["M"])]
-    eC = [float(np.linalg.norm(x - y) / max(np.linalg.norm(x), 1e-300)) for x, y in zip(r["C"], o["C"])]
+    eM = [float(np.linalg.norm(x - y) / max(np.linalg.norm(x), 1e-300)) for x, y in zip(r["M"][:nfr], o["M"][:nfr])]
+    eC = [float(np.linalg.norm(x - y) / max(np.linalg.norm(x), 1e-300)) for x, y in zip(r["C"][:nfr], o["C"][:nfr])]
     print(f"* relative L2 of the fields over the frames (every {int(r['stride'])}-th point): "
           f"M max {max(eM):.2e}, C max {max(eC):.2e}\n")
     print("| frame | step | relL2 M | relL2 C | bit-identical |")
