@@ -46,30 +46,35 @@ def _newer(target, deps):
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def generate():
-    """patched Fortran -> C, both under tests/_build/ (derived files)."""
-    os.makedirs(BUILD, exist_ok=True)
-    patched = os.path.join(BUILD, "PDE-ODEsolver_b200.f90")
-    gen = os.path.join(BUILD, "fortran_host_gen.c")
-    mod = os.path.join(FDIR, "pdeode_b200_mod.f90")
-    deps = [os.path.join(FDIR, "patch_reference.py"), mod, os.path.join(F90C, "f90toc.py"),
-            os.path.join(REF_SRC, "PDE-ODEsolver.f90")]
-    if _newer(gen, deps):
-        subprocess.check_call([sys.executable, os.path.join(FDIR, "patch_reference.py"),
-                               os.path.join(REF_SRC, "PDE-ODEsolver.f90"), "-o", patched], stderr=subprocess.DEVNULL)
-        subprocess.check_call([sys.executable, os.path.join(F90C, "f90toc.py"), "-o", gen, mod, patched,
-                               os.path.join(REF_SRC, "init_random_seed.f90")])
+def _sources():
+    return [os.path.join(FDIR, "patch_reference.py"), os.path.join(FDIR, "pdeode_b200_mod.f90"),
+            os.path.join(F90C, "f90toc.py"), os.path.join(F90C, "f90rt.c"), os.path.join(F90C, "f90rt.h"),
+            os.path.join(REF_SRC, "PDE-ODEsolver.f90"), os.path.join(REF_SRC, "init_random_seed.f90")]
+
+
+def generate(workdir):
+    """patched Fortran -> C inside workdir (derived from the reference: removed after the build,
+    only the executables stay under tests/_build/)."""
+    patched = os.path.join(workdir, "PDE-ODEsolver_b200.f90")
+    gen = os.path.join(workdir, "fortran_host_gen.c")
+    subprocess.check_call([sys.executable, os.path.join(FDIR, "patch_reference.py"),
+                           os.path.join(REF_SRC, "PDE-ODEsolver.f90"), "-o", patched], stderr=subprocess.DEVNULL)
+    subprocess.check_call([sys.executable, os.path.join(F90C, "f90toc.py"), "-o", gen,
+                           os.path.join(FDIR, "pdeode_b200_mod.f90"), patched,
+                           os.path.join(REF_SRC, "init_random_seed.f90")])
     return gen
 
 
 def build(kind):
     """kind = 'cpu' | 'b200'.  Returns the executable (prebuilt one where the sources are absent)."""
+    import shutil
+    import tempfile
     out = exe(kind)
     if not have_sources():
         if not os.path.exists(out):
             raise FileNotFoundError(out + " not prebuilt and /root/reference absent")
         return out
-    gen = generate()
+    os.makedirs(BUILD, exist_ok=True)
     rt = os.path.join(F90C, "f90rt.c")
     if kind == "cpu":
         import oracle_lib as ol
@@ -79,15 +84,19 @@ def build(kind):
         if _newer(so, [ad, os.path.join(ol.ORACLE_DIR, "liboracle.so")]):
             subprocess.check_call([CC, "-O2", "-fPIC", "-shared", "-DADAPTER_EXPORT_ABI", "-o", so, ad,
                                    "-L" + ol.ORACLE_DIR, "-loracle", "-Wl,-rpath," + ol.ORACLE_DIR])
-        if _newer(out, [gen, rt, so]):
-            subprocess.check_call([CC] + CFLAGS + ["-DF90_MAIN", "-o", out, gen, rt, "-L" + BUILD, "-labi_oracle",
-                                                   "-Wl,-rpath,$ORIGIN", "-lm"])
+        deps, link = _sources() + [so], ["-L" + BUILD, "-labi_oracle", "-Wl,-rpath,$ORIGIN"]
     else:
         import __graft_entry__ as ge
         lib = ge.build_cuda()
-        if _newer(out, [gen, rt, lib]):
-            subprocess.check_call([CC] + CFLAGS + ["-DF90_MAIN", "-o", out, gen, rt, "-L" + ge.LIBDIR, "-lpdeode_b200",
-                                                   "-Wl,-rpath,$ORIGIN/../../pde-odesolver_b200/lib", "-lm"])
+        deps, link = _sources() + [lib], ["-L" + ge.LIBDIR, "-lpdeode_b200",
+                                          "-Wl,-rpath,$ORIGIN/../../pde-odesolver_b200/lib"]
+    if _newer(out, deps):
+        work = tempfile.mkdtemp(prefix="fortran_host_")
+        try:
+            gen = generate(work)
+            subprocess.check_call([CC] + CFLAGS + ["-DF90_MAIN", "-o", out, gen, rt] + link + ["-lm"])
+        finally:
+            shutil.rmtree(work, ignore_errors=True)
     return out
 
 
