@@ -77,6 +77,8 @@ def build(kind):
     os.makedirs(BUILD, exist_ok=True)
     rt = os.path.join(F90C, "f90rt.c")
     if kind == "cpu":
+        if HERE not in sys.path:
+            sys.path.insert(0, HERE)
         import oracle_lib as ol
         ol.build_oracle()
         so = os.path.join(BUILD, "libabi_oracle.so")
@@ -86,6 +88,8 @@ def build(kind):
                                    "-L" + ol.ORACLE_DIR, "-loracle", "-Wl,-rpath," + ol.ORACLE_DIR])
         deps, link = _sources() + [so], ["-L" + BUILD, "-labi_oracle", "-Wl,-rpath,$ORIGIN"]
     else:
+        if ROOT not in sys.path:
+            sys.path.insert(0, ROOT)
         import __graft_entry__ as ge
         lib = ge.build_cuda()
         deps, link = _sources() + [lib], ["-L" + ge.LIBDIR, "-lpdeode_b200",
