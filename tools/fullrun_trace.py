@@ -31,6 +31,9 @@ def main():
     ap.add_argument("--frame-every", type=int, default=333)   # filter = int(tEnd/(nOuts*tDel)) (P:638)
     ap.add_argument("--stride", type=int, default=0)          # 0: 2 for <= 512, else 8
     ap.add_argument("--seed", type=int, default=7)
+    ap.add_argument("--perturb", type=float, default=0.0,
+                    help="start from M0 * (1 +- eps), a pseudo-random sign per cell: the size of a "
+                         "rounding difference; shows how far the SAME code drifts from such a start")
     ap.add_argument("--omp", type=int, default=0,
                     help="oracle only: the OpenMP build (the reference's runAll_paral.sh variant) on "
                          "this many threads instead of the serial build")
@@ -44,6 +47,9 @@ def main():
     row = col = args.grid
     stride = args.stride or (2 if row <= 512 else 8)
     M0, C0 = ol.ic_blobs(row, col, 0.02, 0.0390625, 60, args.seed)   # MinitialCond = 5, fixed seed (D5)
+    if args.perturb != 0.0:
+        sign = np.where(np.random.RandomState(12345).randint(0, 2, M0.size) == 1, 1.0, -1.0)
+        M0 = M0 * (1.0 + args.perturb * sign)
     if args.impl == "oracle":
         ol.build_oracle()
         if args.omp > 0:
