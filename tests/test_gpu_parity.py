@@ -68,6 +68,11 @@ def field_tolerance(p, counts_equal, envelope):
       * 1e-9 wherever the GPU took exactly the oracle's CG iteration counts so
         far and the oracle's two builds agree with each other to 1e-10;
       * otherwise 20*e2 (2e-7 at the shipped e2), the size of one CG step.
+    The strict form of the bar lives in tests/test_gpu_serial_order.py: with the reductions in
+    the reference's order (PDEODE_SUM_ORDER=serial) fields and counts are compared with
+    np.array_equal, no tolerance at all.  The measured size of the envelope over full runs --
+    the reference's own code from initial data perturbed in the 14th digit next to the GPU run --
+    is in profiles/r02_fullrun_parity.md.
     """
     if counts_equal and envelope <= 1e-10:
         return TOL_FIELD
