@@ -88,7 +88,8 @@ def test_ic1_slabs_are_slices_of_the_grid(bench):
     M, C = bench.ic1(row, col, 0.9, 0.3)
     assert M.shape == (row * col,) and M.max() <= 0.9 and (C == 1).all()
     import ctypes
-    lib = ctypes.CDLL(os.path.join(ROOT, "pde-odesolver_b200", "lib", "libpdeode_b200.so"))
+    import __graft_entry__ as ge
+    lib = ctypes.CDLL(ge.build_cuda())
     for n in (2, 5, 8):
         parts = []
         for r in range(n):
