@@ -145,3 +145,25 @@ def test_integration_call_sites_match_the_interfaces():
     # components in the order of the type: names match case-insensitively, the last is `reserved` = 0
     given = [a.strip().lower() for a in ctor.group(1).split(",")]
     assert given[:-1] == [n.lower() for _, n in fields[:-1]] and given[-1] == "0"
+
+
+def test_patch_tool_calls_match_the_interfaces():
+    """Every call pde-odesolver_b200/fortran/patch_reference.py inserts into solveOrder2 names an
+    interface of the module and passes as many arguments as it declares."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location(
+        "patch_reference", os.path.join(ROOT, "pde-odesolver_b200", "fortran", "patch_reference.py"))
+    pr = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(pr)
+    _, fields, funcs = parse_module(MOD)
+    text = re.sub(r"&\s*\n\s*", " ", "\n".join([pr.CREATE, pr.MASS, pr.PEAK, pr.FRAME, pr.STEP, pr.FINISH]))
+    calls = re.findall(r"rc = (pdeode_\w+)\(([^)]*)\)", text)
+    assert {c[0] for c in calls} == {"pdeode_create", "pdeode_set_state", "pdeode_mass", "pdeode_peak",
+                                     "pdeode_get_state", "pdeode_step", "pdeode_destroy"}
+    for name, args in calls:
+        assert len([a for a in args.split(",") if a.strip()]) == len(funcs[name][1]), (name, args)
+    ctor = re.search(r"pp = pdeode_params\(([^)]*)\)", text)
+    assert [a.strip().lower() for a in ctor.group(1).split(",")][:-1] == [n.lower() for _, n in fields[:-1]]
+    for decl in ("type(c_ptr) :: ctx", "type(pdeode_params) :: pp", "integer(c_int) :: rc, cnt",
+                 "integer(c_long_long) :: nsum, nmax"):
+        assert decl in pr.DECLS
